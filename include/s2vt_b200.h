@@ -1,0 +1,167 @@
+/*
+ * s2vt_b200.h -- C ABI of libs2vt_b200.so, the sm_100a kernel library underneath the S2VT drop-in.
+ *
+ * The reference (Kamino666/S2VT-video-caption) has no FFI: its hot path is a Python nn.Module whose
+ * arithmetic is delegated to PyTorch library calls (nn.LSTM -> cuDNN/oneDNN, nn.Linear -> cuBLAS/MKL,
+ * nn.CrossEntropyLoss, optim.Adam).  Each entry point below replaces one of those library call sites;
+ * the citation after "replaces:" is the reference file:line (relative to the reference root).
+ *
+ * Conventions
+ *   - plain C, raw DEVICE pointers + sizes, no torch types.  `stream` is a cudaStream_t passed as void*.
+ *   - every call returns 0 on success, non-zero on error; s2vt_last_error() gives the message
+ *     (thread-local).  Nothing throws, nothing calls exit(), nothing synchronises the device.
+ *   - the library allocates nothing: all workspaces are caller-provided.
+ *   - "time-major" means rows ordered (t, b): row = t*B + b.
+ *   - f32 entry points are the exact path (CUDA-core FMA, fp32 operands and accumulation); bf16 entry
+ *     points use tcgen05 tensor cores with fp32 accumulation in TMEM.
+ */
+#ifndef S2VT_B200_H_
+#define S2VT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2VT_ABI_VERSION 1
+
+/* Row addressing of a matrix operand: row m starts at element
+ *     (m / inner) * stride_outer + (m % inner) * stride_inner.
+ * Identity for a dense row-major matrix with leading dimension ld: {1, ld, 0}.
+ * Used to read batch-major [B,L,F] features in time-major order and to write time-major rows into the
+ * batch-major [B,L-1,V] logits the reference API returns (S2VTModel.py:78-81). */
+typedef struct s2vt_rowmap {
+  int32_t inner;
+  int64_t stride_outer;
+  int64_t stride_inner;
+} s2vt_rowmap;
+
+int         s2vt_abi_version(void);
+const char* s2vt_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t     s2vt_launch_count(void);
+/* 1 when the binary carries sm_100a code for the tcgen05 kernels. */
+int         s2vt_has_tcgen05(void);
+
+/* ------------------------------------------------------------------ exact fp32 GEMM (CUDA cores)
+ * C[cmap(m), n] = sum_k A(m,k) * B(n,k) (+ bias[n]) (+ C if accumulate)
+ *   A(m,k) = A[amap(m) + k]            if !a_trans  (K contiguous)
+ *          = A[k * lda_t + m]          if  a_trans  (M contiguous; amap ignored)
+ *   B(n,k) = B[n * ldb + k]            if !b_trans  (weight layout [N,K], as nn.Linear stores it)
+ *          = B[k * ldb + n]            if  b_trans
+ *   split_k > 1: slice z of K writes its partial product to C + z * split_stride (no bias/accumulate).
+ * replaces: nn.Linear / addmm at S2VTModel.py:54,80 and the input-side and recurrent products inside
+ * nn.LSTM at S2VTModel.py:57,60,67,77,86,93,103, plus their autograd transposes (train.py:124). */
+int s2vt_gemm_f32(void* stream, int M, int N, int K,
+                  const float* A, s2vt_rowmap amap, int a_trans, int64_t lda_t,
+                  const float* B, int64_t ldb, int b_trans,
+                  float* C, s2vt_rowmap cmap,
+                  const float* bias, int accumulate, int split_k, int64_t split_stride);
+
+/* ------------------------------------------------------------------ bf16 tcgen05 GEMM (tensor cores)
+ * Same contract as s2vt_gemm_f32 with bf16 operands, fp32 accumulation in TMEM, fed by TMA.
+ *   a_mn_major / b_mn_major: operand stored with its M (resp. N) index contiguous ([K,M] / [K,N]).
+ *   out_bf16: C is bf16 instead of f32.   lda / ldb are leading dimensions in elements.
+ * tensor maps are encoded per call on the host (cuTensorMapEncodeTiled) -- pointers must be 16 B
+ * aligned and leading dimensions multiples of 8 elements. */
+int s2vt_gemm_bf16(void* stream, int M, int N, int K,
+                   const void* A, int64_t lda, int a_mn_major,
+                   const void* B, int64_t ldb, int b_mn_major,
+                   void* C, s2vt_rowmap cmap, int out_bf16,
+                   const float* bias, int accumulate);
+
+/* f32 -> bf16 cast (optionally also writes the transpose: dst_t[c, r] = src[r, c]). */
+int s2vt_cast_bf16(void* stream, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols);
+
+/* ------------------------------------------------------------------ LSTM recurrence, exact fp32
+ * One nn.LSTM layer (num_layers=1, unidirectional, batch_first handled by the caller) over T steps.
+ *   pre      [n_pre, B, 4H]  input-side pre-activations W_ih x_t + b_ih + b_hh for t < n_pre
+ *   bias_sum [4H]            b_ih + b_hh, used alone for t >= n_pre (the reference's zero padding,
+ *                            S2VTModel.py:64-65 / 208-210)
+ *   w_hh     [4H, H]         gate row blocks i,f,g,o
+ *   h0,c0    [B,H] or NULL (zero state)
+ *   out      [T, B, H]       h_t, time-major
+ *   gates    [T, B, 4H] or NULL   post-activation i,f,g,o stash for BPTT
+ *   cells    [T, B, H]  or NULL   c_t stash for BPTT
+ *   hT,cT    [B,H] or NULL   final state
+ *   ws       >= s2vt_lstm_ws_bytes(B,H) bytes of scratch
+ * replaces: self.vid_rnn(...) / self.word_rnn(...) at S2VTModel.py:57,60,67,77,86. */
+int64_t s2vt_lstm_ws_bytes(int B, int H);
+int s2vt_lstm_fwd_f32(void* stream, int T, int B, int H, int n_pre,
+                      const float* pre, const float* bias_sum, const float* w_hh,
+                      const float* h0, const float* c0,
+                      float* out, float* gates, float* cells, float* hT, float* cT, void* ws);
+
+/* BPTT through one layer from a zero final-state gradient.
+ *   dout   [T, B, H]  dL/dh_t from above; rows t < dout_t0 are treated as zero (and not read)
+ *   gates, cells      the forward stash;  c0 = 0 is assumed (the reference never passes a state in training)
+ *   dgates [T, B, 4H] out: gradient w.r.t. the pre-activations
+ * replaces: autograd of nn.LSTM under loss.backward(), train.py:124. */
+int s2vt_lstm_bwd_f32(void* stream, int T, int B, int H, int dout_t0,
+                      const float* dout, const float* gates, const float* cells, const float* w_hh,
+                      float* dgates, void* ws);
+
+/* ------------------------------------------------------------------ embedding
+ * out[t*B + b, :] = table[ids[b*ids_ld + t], :]   for t < n_t    (time-major gather)
+ * replaces: self.embedding(targets), S2VTModel.py:71. */
+int s2vt_embed_gather_f32(void* stream, const float* table, int E, const int64_t* ids, int64_t ids_ld,
+                          int B, int n_t, float* out, int64_t out_ld);
+/* grad_table[ids[b*ids_ld+t], :] += src[t*B + b, 0:E]  (dense grad, like nn.Embedding sparse=False) */
+int s2vt_embed_scatter_add_f32(void* stream, float* grad_table, int E, const int64_t* ids, int64_t ids_ld,
+                               int B, int n_t, const float* src, int64_t src_ld);
+
+/* column sums: out[n] (+)= sum_m X[m*ld + n]; bias gradients. */
+int s2vt_colsum_f32(void* stream, const float* X, int64_t M, int N, int64_t ld, float* out, int accumulate);
+
+/* ------------------------------------------------------------------ loss
+ * Mean cross entropy over R rows of V logits (the effective MaskCriterion, utils.py:13-26: the mask
+ * cancels because nn.CrossEntropyLoss() already reduced to a scalar mean).
+ *   logits [R, V] f32 row-major;  target row r = targets[(r / t_inner) * t_so + (r % t_inner) * t_si]
+ *   row_loss [R] scratch;  loss: 1 float out;  dlogits: NULL, or [R,V] out = (softmax - onehot) * gscale[0] / R
+ *   (dlogits may alias logits).  gscale: device pointer to the upstream scalar gradient, NULL = 1. */
+int s2vt_ce_f32(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
+                float* row_loss, float* loss, float* dlogits, const float* gscale);
+
+/* ------------------------------------------------------------------ Adam
+ * torch.optim.Adam step (train.py:89-93,125) over a flat buffer; step_count is the 1-based step index.
+ * bf16_copy (nullable): refreshed bf16 shadow of the updated parameters. */
+int s2vt_adam_f32(void* stream, float* p, const float* g, float* m, float* v, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step_count, float grad_scale,
+                  void* bf16_copy);
+
+/* ------------------------------------------------------------------ greedy decode, exact fp32
+ * The decode loop of S2VT.forward(mode='test'), S2VTModel.py:88-110.
+ *   pre2_vid [n_steps, B, 4H]  vid-half pre-activations of word_rnn for the decode steps
+ *                              (W_ih[:, E:] output1_t + b_ih + b_hh)
+ *   w_cat    [4H, E+H]         [ W_ih[:, :E] | W_hh ] of word_rnn
+ *   h2,c2    [B,H]             word_rnn state after the encode stage (updated in place)
+ *   tokens   [B, n_steps] i64  out (batch-major, as the reference returns)
+ *   ws       >= s2vt_greedy_ws_bytes(B,H,E,V) */
+int64_t s2vt_greedy_ws_bytes(int B, int H, int E, int V);
+int s2vt_greedy_decode_f32(void* stream, int B, int H, int E, int V, int n_steps, int sos_ix,
+                           const float* pre2_vid, const float* w_cat, const float* emb,
+                           const float* w_out, const float* b_out,
+                           float* h2, float* c2, int64_t* tokens, void* ws);
+
+/* ------------------------------------------------------------------ beam search, exact fp32
+ * S2VT.beam_search, S2VTModel.py:149-240, in lock-step over all videos and beams.
+ *   state    [4, B, H]   h1,c1,h2,c2 after the encode stage (S2VTModel.py:57-60)
+ *   bias1    [4H]        vid_rnn b_ih+b_hh (its input is the zero pad, S2VTModel.py:208-210)
+ *   w_hh1    [4H,H];  w_cat2 [4H, E+H+H] = [ W_ih2[:, :E] | W_ih2[:, E:] | W_hh2 ];  bias2 [4H]
+ *   len_pen  [max_depth+2] host-computed float(pow(float(n), 0.7)) table (BeamSearchNode.eval)
+ *   out_tokens [B, max_depth+1] i64, -1 padded, <sos> first;  out_len [B] i32
+ *   topk: the reference expands top-20 (S2VTModel.py:216)
+ *   ws >= s2vt_beam_ws_bytes(...) */
+int64_t s2vt_beam_ws_bytes(int B, int H, int E, int V, int beam_width, int max_depth, int topk);
+int s2vt_beam_search_f32(void* stream, int B, int H, int E, int V, int beam_width, int max_depth, int topk,
+                         int sos_ix, int eos_ix,
+                         const float* state, const float* bias1, const float* w_hh1,
+                         const float* w_cat2, const float* bias2, const float* emb,
+                         const float* w_out, const float* b_out, const float* len_pen,
+                         int64_t* out_tokens, int32_t* out_len, void* ws);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2VT_B200_H_ */
