@@ -43,19 +43,22 @@ const char* s2vt_last_error(void);
 int64_t     s2vt_launch_count(void);
 /* 1 when the binary carries sm_100a code for the tcgen05 kernels. */
 int         s2vt_has_tcgen05(void);
+/* Debug aid: synchronises `stream` and returns the device-side error flag of the tensor-core kernels
+ * (0 = none; non-zero = an mbarrier wait timed out, which is never expected). */
+int         s2vt_device_error_flag(void* stream);
 
 /* ------------------------------------------------------------------ exact fp32 GEMM (CUDA cores)
  * C[cmap(m), n] = sum_k A(m,k) * B(n,k) (+ bias[n]) (+ C if accumulate)
  *   A(m,k) = A[amap(m) + k]            if !a_trans  (K contiguous)
- *          = A[k * lda_t + m]          if  a_trans  (M contiguous; amap ignored)
- *   B(n,k) = B[n * ldb + k]            if !b_trans  (weight layout [N,K], as nn.Linear stores it)
- *          = B[k * ldb + n]            if  b_trans
+ *          = A[amap(k) + m]            if  a_trans  (M contiguous; amap addresses the K index)
+ *   B(n,k) = B[bmap(n) + k]            if !b_trans  (weight layout [N,K], as nn.Linear stores it)
+ *          = B[bmap(k) + n]            if  b_trans
  *   split_k > 1: slice z of K writes its partial product to C + z * split_stride (no bias/accumulate).
  * replaces: nn.Linear / addmm at S2VTModel.py:54,80 and the input-side and recurrent products inside
  * nn.LSTM at S2VTModel.py:57,60,67,77,86,93,103, plus their autograd transposes (train.py:124). */
 int s2vt_gemm_f32(void* stream, int M, int N, int K,
-                  const float* A, s2vt_rowmap amap, int a_trans, int64_t lda_t,
-                  const float* B, int64_t ldb, int b_trans,
+                  const float* A, s2vt_rowmap amap, int a_trans,
+                  const float* B, s2vt_rowmap bmap, int b_trans,
                   float* C, s2vt_rowmap cmap,
                   const float* bias, int accumulate, int split_k, int64_t split_stride);
 
@@ -110,6 +113,9 @@ int s2vt_embed_gather_f32(void* stream, const float* table, int E, const int64_t
 /* grad_table[ids[b*ids_ld+t], :] += src[t*B + b, 0:E]  (dense grad, like nn.Embedding sparse=False) */
 int s2vt_embed_scatter_add_f32(void* stream, float* grad_table, int E, const int64_t* ids, int64_t ids_ld,
                                int B, int n_t, const float* src, int64_t src_ld);
+
+/* out[i] = a[i] + b[i]  (b_ih + b_hh) */
+int s2vt_add_f32(void* stream, const float* a, const float* b, float* out, int64_t n);
 
 /* column sums: out[n] (+)= sum_m X[m*ld + n]; bias gradients. */
 int s2vt_colsum_f32(void* stream, const float* X, int64_t M, int N, int64_t ld, float* out, int accumulate);

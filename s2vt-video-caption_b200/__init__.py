@@ -1,0 +1,9 @@
+"""s2vt-video-caption_b200: B200-native (sm_100a) drop-in for the S2VT encoder-decoder hot path of
+Kamino666/S2VT-video-caption.  Import through the `s2vt_b200` shim at the repo root."""
+from .criterion import MaskCriterion
+from .lib import LIB_PATH, S2VTLibraryError, launch_count, load
+from .model import PARAM_ORDER, S2VT, S2VTModel
+from .optim import FusedAdam
+
+__all__ = ["S2VT", "S2VTModel", "MaskCriterion", "FusedAdam", "PARAM_ORDER", "load", "launch_count", "LIB_PATH",
+           "S2VTLibraryError"]

@@ -1,0 +1,418 @@
+"""Drop-in S2VT module: the reference's constructor / forward / state_dict contract
+(S2VTModel.py:10-110, 149-240) with the arithmetic executed by libs2vt_b200.so.
+
+    model = S2VT(vocab_size, feat_dim, length, dim_hid=512, dim_embed=512).cuda()
+    logits = model(feats, targets=targets[:, :-1], mode='train')      # train.py:120
+    tokens = model(feats, mode='test')                                  # eval.py:52
+    sents  = model(feats, mode='beam_search')                           # eval.py:88
+
+Only what the reference's Opt() permits is supported (LSTM, one layer, unidirectional, dropout 0);
+anything else raises NotImplementedError -- there is no cuDNN / CPU fallback on this path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .lib import dense, rowmap, require_cuda
+
+PARAM_ORDER = (
+    "vid_rnn.weight_ih_l0", "vid_rnn.weight_hh_l0", "vid_rnn.bias_ih_l0", "vid_rnn.bias_hh_l0",
+    "word_rnn.weight_ih_l0", "word_rnn.weight_hh_l0", "word_rnn.bias_ih_l0", "word_rnn.bias_hh_l0",
+    "feat_linear.weight", "feat_linear.bias", "out_linear.weight", "out_linear.bias",
+    "embedding.weight",
+)
+
+
+# --------------------------------------------------------------------------- parameter holders
+class _LSTMParams(nn.Module):
+    """Holds the four tensors of a 1-layer unidirectional nn.LSTM under the same names
+    (weight_ih_l0 [4H,I], weight_hh_l0 [4H,H], bias_ih_l0, bias_hh_l0; gate rows i,f,g,o) and with
+    nn.LSTM's init (U(+-1/sqrt(H)) drawn in registration order), S2VTModel.py:19-22."""
+
+    def __init__(self, input_size: int, hidden_size: int):
+        super().__init__()
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.weight_ih_l0 = nn.Parameter(torch.empty(4 * hidden_size, input_size))
+        self.weight_hh_l0 = nn.Parameter(torch.empty(4 * hidden_size, hidden_size))
+        self.bias_ih_l0 = nn.Parameter(torch.empty(4 * hidden_size))
+        self.bias_hh_l0 = nn.Parameter(torch.empty(4 * hidden_size))
+        k = 1.0 / math.sqrt(hidden_size) if hidden_size > 0 else 0.0
+        for p in self.parameters():
+            nn.init.uniform_(p, -k, k)
+
+    def extra_repr(self):
+        return "%d, %d, batch_first=True (sm_100a kernels)" % (self.input_size, self.hidden_size)
+
+
+class _LinearParams(nn.Module):
+    """weight [out,in] + bias [out] with nn.Linear's default init, S2VTModel.py:26-27."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(in_features) if in_features > 0 else 0.0
+        nn.init.uniform_(self.bias, -bound, bound)
+
+    def extra_repr(self):
+        return "in_features=%d, out_features=%d (sm_100a kernels)" % (self.in_features, self.out_features)
+
+
+class _EmbeddingParams(nn.Module):
+    """weight [V,E] ~ N(0,1) like nn.Embedding, S2VTModel.py:28 (dense gradient)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int):
+        super().__init__()
+        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+        self.weight = nn.Parameter(torch.empty(num_embeddings, embedding_dim))
+        nn.init.normal_(self.weight)
+
+    def extra_repr(self):
+        return "%d, %d (sm_100a kernels)" % (self.num_embeddings, self.embedding_dim)
+
+
+# --------------------------------------------------------------------------- fp32 engine
+def _bias_sums(P):
+    dev = P["vid_rnn.bias_ih_l0"].device
+    b1 = ops.add_f32(P["vid_rnn.bias_ih_l0"], P["vid_rnn.bias_hh_l0"], torch.empty_like(P["vid_rnn.bias_ih_l0"], device=dev))
+    b2 = ops.add_f32(P["word_rnn.bias_ih_l0"], P["word_rnn.bias_hh_l0"], torch.empty_like(P["word_rnn.bias_ih_l0"], device=dev))
+    return b1, b2
+
+
+def _encode_vid_f32(P, feats, T: int, stash: bool, b1):
+    """feat_linear + vid_rnn over T steps (S2VTModel.py:52-67; T=L for beam search, S2VTModel.py:57)."""
+    B, L, F = feats.shape
+    H = P["vid_rnn.weight_hh_l0"].shape[1]
+    dev = feats.device
+    xproj = torch.empty(L * B, H, device=dev)
+    # time-major rows (t,b) read from the batch-major [B,L,F] input
+    ops.gemm_f32(L * B, H, F, feats, rowmap(B, F, L * F), False, P["feat_linear.weight"], dense(F), False, xproj, dense(H),
+                 bias=P["feat_linear.bias"])
+    pre1 = torch.empty(L * B, 4 * H, device=dev)
+    ops.gemm_f32(L * B, 4 * H, H, xproj, dense(H), False, P["vid_rnn.weight_ih_l0"], dense(H), False, pre1, dense(4 * H), bias=b1)
+    out1 = torch.empty(T * B, H, device=dev)
+    g1 = torch.empty(T * B, 4 * H, device=dev) if stash else None
+    c1 = torch.empty(T * B, H, device=dev) if stash else None
+    hT = torch.empty(B, H, device=dev)
+    cT = torch.empty(B, H, device=dev)
+    ops.lstm_fwd_f32(T, B, H, min(L, T), pre1, b1, P["vid_rnn.weight_hh_l0"], out1, g1, c1, hT=hT, cT=cT)
+    return xproj, out1, g1, c1, hT, cT
+
+
+def _word_pre_vid_f32(P, out1, rows: int, b2, E: int, H: int):
+    """vid half of word_rnn's input product: out1 . W_ih[:, E:]^T + (b_ih + b_hh)  (S2VTModel.py:75: embedding columns first)."""
+    pre2 = torch.empty(rows, 4 * H, device=out1.device)
+    ops.gemm_f32(rows, 4 * H, H, out1, dense(H), False, P["word_rnn.weight_ih_l0"], dense(E + H), False, pre2, dense(4 * H),
+                 bias=b2, b_off=E)
+    return pre2
+
+
+def train_forward_f32(P: Dict[str, torch.Tensor], feats: torch.Tensor, targets: torch.Tensor, stash: bool, batch_major_logits: bool):
+    """S2VT.forward(mode='train') in exact fp32.  Returns (logits, saved)."""
+    B, L, F = feats.shape
+    H = P["vid_rnn.weight_hh_l0"].shape[1]
+    V, E = P["embedding.weight"].shape
+    T = 2 * L - 1
+    dev = feats.device
+    b1, b2 = _bias_sums(P)
+    xproj, out1, g1, c1, _, _ = _encode_vid_f32(P, feats, T, stash, b1)
+    emb_seq = torch.empty((L - 1) * B, E, device=dev)
+    ops.embed_gather_f32(P["embedding.weight"], targets, 0, L - 1, B, L - 1, emb_seq, E)
+    pre2 = _word_pre_vid_f32(P, out1, T * B, b2, E, H)
+    # embedding half only exists for the decode steps t >= L (pad_embed is zero before, S2VTModel.py:72-73)
+    ops.gemm_f32((L - 1) * B, 4 * H, E, emb_seq, dense(E), False, P["word_rnn.weight_ih_l0"], dense(E + H), False, pre2,
+                 dense(4 * H), accumulate=True, c_off=L * B * 4 * H)
+    out2 = torch.empty(T * B, H, device=dev)
+    g2 = torch.empty(T * B, 4 * H, device=dev) if stash else None
+    c2 = torch.empty(T * B, H, device=dev) if stash else None
+    ops.lstm_fwd_f32(T, B, H, T, pre2, b2, P["word_rnn.weight_hh_l0"], out2, g2, c2)
+    R = (L - 1) * B
+    if batch_major_logits:
+        logits = torch.empty(B, L - 1, V, device=dev)
+        cmap = rowmap(B, V, (L - 1) * V)                 # row (t,b) -> [b, t, :]
+    else:
+        logits = torch.empty(R, V, device=dev)
+        cmap = dense(V)
+    ops.gemm_f32(R, V, H, out2, dense(H), False, P["out_linear.weight"], dense(H), False, logits, cmap, bias=P["out_linear.bias"],
+                 a_off=L * B * H)
+    saved = dict(xproj=xproj, out1=out1, g1=g1, c1=c1, out2=out2, g2=g2, c2=c2, emb_seq=emb_seq, dims=(B, L, F, H, E, V, T)) if stash else None
+    return logits, saved
+
+
+def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_major: bool, need_dfeats: bool):
+    """BPTT for train_forward_f32: dl = dL/dlogits ([B,L-1,V] batch-major or [(L-1)B,V] time-major).
+    Returns grads in PARAM_ORDER (+ dfeats or None)."""
+    B, L, F, H, E, V, T = saved["dims"]
+    dev = dl.device
+    R = (L - 1) * B
+    out1, out2 = saved["out1"], saved["out2"]
+    G = {}
+    hdec_off = L * B * H
+    # ---- out_linear
+    gW = torch.empty(V, H, device=dev)
+    if dl_batch_major:
+        # K runs over batch-major rows k = b*(L-1)+t; the matching h row is (L+t)*B + b
+        ops.gemm_f32(V, H, R, dl, dense(V), True, out2, rowmap(L - 1, H, B * H), True, gW, dense(H), b_off=hdec_off)
+        amap_rows = rowmap(B, V, (L - 1) * V)
+    else:
+        ops.gemm_f32(V, H, R, dl, dense(V), True, out2, dense(H), True, gW, dense(H), b_off=hdec_off)
+        amap_rows = dense(V)
+    G["out_linear.weight"] = gW
+    gb = torch.empty(V, device=dev)
+    ops.colsum_f32(dl, R, V, V, gb)
+    G["out_linear.bias"] = gb
+    dout2 = torch.empty(T * B, H, device=dev)          # rows < L*B are never read (dout_t0 = L)
+    ops.gemm_f32(R, H, V, dl, amap_rows, False, P["out_linear.weight"], dense(H), True, dout2, dense(H), c_off=hdec_off)
+    # ---- word_rnn
+    dg2 = torch.empty(T * B, 4 * H, device=dev)
+    ops.lstm_bwd_f32(T, B, H, L, dout2, saved["g2"], saved["c2"], P["word_rnn.weight_hh_l0"], dg2)
+    gWih2 = torch.empty(4 * H, E + H, device=dev)
+    ops.gemm_f32(4 * H, H, T * B, dg2, dense(4 * H), True, out1, dense(H), True, gWih2, dense(E + H), c_off=E)
+    ops.gemm_f32(4 * H, E, R, dg2, dense(4 * H), True, saved["emb_seq"], dense(E), True, gWih2, dense(E + H), a_off=L * B * 4 * H)
+    G["word_rnn.weight_ih_l0"] = gWih2
+    gWhh2 = torch.empty(4 * H, H, device=dev)
+    ops.gemm_f32(4 * H, H, (T - 1) * B, dg2, dense(4 * H), True, out2, dense(H), True, gWhh2, dense(H), a_off=B * 4 * H)
+    G["word_rnn.weight_hh_l0"] = gWhh2
+    gb2 = torch.empty(4 * H, device=dev)
+    ops.colsum_f32(dg2, T * B, 4 * H, 4 * H, gb2)
+    G["word_rnn.bias_ih_l0"] = gb2
+    G["word_rnn.bias_hh_l0"] = gb2.clone()
+    # d input2 = dg2 . W_ih2: vid half -> dL/d output1, embedding half -> dense embedding grad
+    dout1 = torch.empty(T * B, H, device=dev)
+    ops.gemm_f32(T * B, H, 4 * H, dg2, dense(4 * H), False, P["word_rnn.weight_ih_l0"], dense(E + H), True, dout1, dense(H), b_off=E)
+    demb = torch.empty(R, E, device=dev)
+    ops.gemm_f32(R, E, 4 * H, dg2, dense(4 * H), False, P["word_rnn.weight_ih_l0"], dense(E + H), True, demb, dense(E),
+                 a_off=L * B * 4 * H)
+    gE = torch.zeros(V, E, device=dev)
+    ops.embed_scatter_add_f32(gE, targets, 0, L - 1, B, L - 1, demb, E)
+    G["embedding.weight"] = gE
+    # ---- vid_rnn
+    dg1 = torch.empty(T * B, 4 * H, device=dev)
+    ops.lstm_bwd_f32(T, B, H, 0, dout1, saved["g1"], saved["c1"], P["vid_rnn.weight_hh_l0"], dg1)
+    gWih1 = torch.empty(4 * H, H, device=dev)
+    ops.gemm_f32(4 * H, H, L * B, dg1, dense(4 * H), True, saved["xproj"], dense(H), True, gWih1, dense(H))
+    G["vid_rnn.weight_ih_l0"] = gWih1
+    gWhh1 = torch.empty(4 * H, H, device=dev)
+    ops.gemm_f32(4 * H, H, (T - 1) * B, dg1, dense(4 * H), True, out1, dense(H), True, gWhh1, dense(H), a_off=B * 4 * H)
+    G["vid_rnn.weight_hh_l0"] = gWhh1
+    gb1 = torch.empty(4 * H, device=dev)
+    ops.colsum_f32(dg1, T * B, 4 * H, 4 * H, gb1)
+    G["vid_rnn.bias_ih_l0"] = gb1
+    G["vid_rnn.bias_hh_l0"] = gb1.clone()
+    # ---- feat_linear
+    dxp = torch.empty(L * B, H, device=dev)
+    ops.gemm_f32(L * B, H, 4 * H, dg1, dense(4 * H), False, P["vid_rnn.weight_ih_l0"], dense(H), True, dxp, dense(H))
+    gWf = torch.empty(H, F, device=dev)
+    ops.gemm_f32(H, F, L * B, dxp, dense(H), True, feats, rowmap(B, F, L * F), True, gWf, dense(F))
+    G["feat_linear.weight"] = gWf
+    gbf = torch.empty(H, device=dev)
+    ops.colsum_f32(dxp, L * B, H, H, gbf)
+    G["feat_linear.bias"] = gbf
+    dfeats = None
+    if need_dfeats:                                     # dataloader.py:38 makes feats require grad
+        dfeats = torch.empty(B, L, F, device=dev)
+        ops.gemm_f32(L * B, F, H, dxp, dense(H), False, P["feat_linear.weight"], dense(F), True, dfeats, rowmap(B, F, L * F))
+    return [G[k] for k in PARAM_ORDER], dfeats
+
+
+class _TrainLogitsFn(torch.autograd.Function):
+    """forward(mode='train') -> materialised fp32 logits [B,L-1,V], differentiable (train.py:120-124)."""
+
+    @staticmethod
+    def forward(ctx, feats, targets, *params):
+        P = dict(zip(PARAM_ORDER, params))
+        need = any(ctx.needs_input_grad)
+        logits, saved = train_forward_f32(P, feats, targets, stash=need, batch_major_logits=True)
+        ctx.saved, ctx.P, ctx.feats, ctx.targets = saved, P, feats, targets
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        dl = dl.contiguous()
+        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.targets, dl, True, ctx.needs_input_grad[0])
+        ctx.saved = None
+        return (dfeats, None) + tuple(grads)
+
+
+class _TrainLossFn(torch.autograd.Function):
+    """Fused forward + MaskCriterion (utils.py:13-26) without handing the logits to autograd."""
+
+    @staticmethod
+    def forward(ctx, feats, targets_full, *params):
+        P = dict(zip(PARAM_ORDER, params))
+        B, L, _ = feats.shape
+        V = P["embedding.weight"].shape[0]
+        need = any(ctx.needs_input_grad)
+        tin = targets_full[:, :-1].contiguous()
+        logits, saved = train_forward_f32(P, feats, tin, stash=need, batch_major_logits=False)
+        loss = torch.empty((), device=feats.device)
+        # row (t,b) of the time-major logits is scored against targets_full[b, t+1]
+        ops.ce_f32(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss)
+        ctx.saved, ctx.P, ctx.feats, ctx.tin, ctx.tfull, ctx.logits = saved, P, feats, tin, targets_full, logits
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        B, L, _ = ctx.feats.shape
+        V = ctx.P["embedding.weight"].shape[0]
+        logits = ctx.logits
+        scratch = torch.empty((), device=logits.device)
+        g = gloss.contiguous().to(torch.float32)
+        ops.ce_f32(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), scratch, dlogits=logits, gscale=g)
+        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.tin, logits, False, ctx.needs_input_grad[0])
+        ctx.saved = ctx.logits = None
+        return (dfeats, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------------- the module
+class S2VT(nn.Module):
+    def __init__(self, vocab_size, feat_dim, length, dim_hid=500, dim_embed=500, feat_dropout=0, rnn_dropout=0,
+                 out_dropout=0, num_layers=1, bidirectional=False, rnn_type='lstm', sos_ix=3, eos_ix=4,
+                 train_precision: str = "fp32", decode_precision: str = "fp32"):
+        super().__init__()
+        if str(rnn_type).lower() != 'lstm':
+            raise NotImplementedError("only rnn_type='lstm' is supported (the reference warns against GRU, train.py:35)")
+        if num_layers != 1 or bidirectional:
+            raise NotImplementedError("only num_layers=1, bidirectional=False is supported (train.py:33-34)")
+        if feat_dropout or rnn_dropout or out_dropout:
+            raise NotImplementedError("dropout > 0 is not supported on the sm_100a path (Opt() uses 0, train.py:30-32)")
+        # construction order == the reference's, so a seeded construction draws identical weights
+        self.vid_rnn = _LSTMParams(dim_hid, dim_hid)
+        self.word_rnn = _LSTMParams(dim_hid + dim_embed, dim_hid)
+        self.feat_linear = _LinearParams(feat_dim, dim_hid)
+        self.out_linear = _LinearParams(dim_hid, vocab_size)
+        self.embedding = _EmbeddingParams(vocab_size, dim_embed)
+        self.feat_dim = feat_dim
+        self.length = length
+        self.dim_hid = dim_hid
+        self.dim_embed = dim_embed
+        self.sos_ix = sos_ix
+        self.eos_ix = eos_ix
+        self.vocab_size = vocab_size
+        self.rnn_type = rnn_type
+        self.train_precision = train_precision
+        self.decode_precision = decode_precision
+        self.beam_topk = 20                     # S2VTModel.py:216
+
+    # ---- helpers
+    def _params(self) -> Dict[str, torch.Tensor]:
+        sd = dict(self.named_parameters())
+        return {k: sd[k] for k in PARAM_ORDER}
+
+    def _check_inputs(self, feats: torch.Tensor):
+        if feats.dim() != 3 or feats.shape[1] != self.length or feats.shape[2] != self.feat_dim:
+            raise ValueError("feats must be [B, %d, %d] (got %s)" % (self.length, self.feat_dim, tuple(feats.shape)))
+        require_cuda(feats, self.embedding.weight)
+        if feats.dtype != torch.float32:
+            raise ValueError("feats must be float32")
+        if str(self.rnn_type).lower() != 'lstm':
+            raise NotImplementedError("only rnn_type='lstm' is supported")
+
+    def forward(self, feats, targets=None, mode='train', beam_width=3, max_beam_depth=30):
+        """
+        :param feats: [B, L, feat_dim] float32 (CUDA)
+        :param targets: [B, L-1] int64 (mode='train')
+        :param mode: train: fixed-length teacher forcing -> logits [B, L-1, V]
+                     test: greedy -> int64 [B, L-1]   beam_search: list[B] of list[Tensor], <sos> first
+        """
+        self._check_inputs(feats)
+        feats = feats.contiguous()
+        if mode == 'train':
+            if targets is None:
+                raise ValueError("mode='train' needs targets [B, L-1]")
+            if targets.dim() != 2 or targets.shape[0] != feats.shape[0] or targets.shape[1] != self.length - 1:
+                raise RuntimeError("targets must be [B, length-1] = [%d, %d] (got %s); the reference fails in torch.cat "
+                                   "(S2VTModel.py:73-75)" % (feats.shape[0], self.length - 1, tuple(targets.shape)))
+            targets = targets.contiguous().to(torch.int64)
+            P = self._params()
+            return _TrainLogitsFn.apply(feats, targets, *[P[k] for k in PARAM_ORDER])
+        elif mode == 'test':
+            with torch.no_grad():
+                return self._greedy(feats.detach())
+        elif mode == 'beam_search':
+            with torch.no_grad():
+                toks, lens = self.beam_search_ids(feats.detach(), beam_width=beam_width, max_beam_depth=max_beam_depth)
+            return self._ids_to_reference_lists(toks, lens)
+        raise ValueError("unknown mode %r" % (mode,))
+
+    def forward_loss(self, feats, targets, mask=None):
+        """Fused train forward + MaskCriterion: returns the scalar the reference computes with
+        criterion(model(feats, targets[:, :-1], 'train'), targets, mask) (train.py:120-122) without
+        materialising [B,L-1,V] logits for autograd.  `mask` is accepted for signature parity; the
+        reference's criterion is independent of it (utils.py:19-26)."""
+        self._check_inputs(feats)
+        if targets.dim() != 2 or targets.shape[1] != self.length:
+            raise RuntimeError("targets must be [B, length] (got %s)" % (tuple(targets.shape),))
+        P = self._params()
+        return _TrainLossFn.apply(feats.contiguous(), targets.contiguous().to(torch.int64), *[P[k] for k in PARAM_ORDER])
+
+    # ---- greedy (S2VTModel.py:82-110)
+    def _greedy(self, feats):
+        P = {k: v.detach() for k, v in self._params().items()}
+        B, L, _ = feats.shape
+        H, E, V = self.dim_hid, self.dim_embed, self.vocab_size
+        T = 2 * L - 1
+        dev = feats.device
+        b1, b2 = _bias_sums(P)
+        _, out1, _, _, _, _ = _encode_vid_f32(P, feats, T, False, b1)
+        pre2 = _word_pre_vid_f32(P, out1, T * B, b2, E, H)
+        enc2 = torch.empty(L * B, H, device=dev)
+        h2 = torch.empty(B, H, device=dev)
+        c2 = torch.empty(B, H, device=dev)
+        ops.lstm_fwd_f32(L, B, H, L, pre2, b2, P["word_rnn.weight_hh_l0"], enc2, hT=h2, cT=c2)
+        w_cat = torch.cat([P["word_rnn.weight_ih_l0"][:, :E], P["word_rnn.weight_hh_l0"]], dim=1).contiguous()
+        tokens = torch.empty(B, L - 1, dtype=torch.int64, device=dev)
+        ops.greedy_decode_f32(B, H, E, V, L - 1, int(self.sos_ix), pre2, L * B * 4 * H, w_cat, P["embedding.weight"],
+                              P["out_linear.weight"], P["out_linear.bias"], h2, c2, tokens)
+        return tokens
+
+    # ---- beam search (S2VTModel.py:56-61, 149-240)
+    def beam_search_ids(self, feats, beam_width=3, max_beam_depth=30):
+        """Beam search returning (tokens int64 [B, max_depth+1] padded with -1, lengths int32 [B]); row b holds
+        what the reference returns as sentences[b], <sos> first."""
+        self._check_inputs(feats)
+        feats = feats.contiguous()
+        P = {k: v.detach() for k, v in self._params().items()}
+        B, L, _ = feats.shape
+        H, E, V = self.dim_hid, self.dim_embed, self.vocab_size
+        dev = feats.device
+        if V < self.beam_topk:
+            raise RuntimeError("beam search expands topk(%d) (S2VTModel.py:216): vocab_size must be >= %d" % (self.beam_topk, self.beam_topk))
+        b1, b2 = _bias_sums(P)
+        _, out1, _, _, h1, c1 = _encode_vid_f32(P, feats, L, False, b1)
+        pre2 = _word_pre_vid_f32(P, out1, L * B, b2, E, H)
+        enc2 = torch.empty(L * B, H, device=dev)
+        state = torch.empty(4, B, H, device=dev)
+        state[0].copy_(h1); state[1].copy_(c1)
+        ops.lstm_fwd_f32(L, B, H, L, pre2, b2, P["word_rnn.weight_hh_l0"], enc2, hT=state[2], cT=state[3])
+        w_cat2 = torch.cat([P["word_rnn.weight_ih_l0"], P["word_rnn.weight_hh_l0"]], dim=1).contiguous()
+        # BeamSearchNode.eval: logp / pow(float(leng), 0.7) -- divisor computed in Python double precision
+        pen = torch.tensor([0.0] + [pow(float(n), 0.7) for n in range(1, max_beam_depth + 3)], dtype=torch.float32).to(dev)
+        toks = torch.empty(B, max_beam_depth + 1, dtype=torch.int64, device=dev)
+        lens = torch.empty(B, dtype=torch.int32, device=dev)
+        ops.beam_search_f32(B, H, E, V, int(beam_width), int(max_beam_depth), self.beam_topk, int(self.sos_ix), int(self.eos_ix),
+                            state, b1, P["vid_rnn.weight_hh_l0"], w_cat2, b2, P["embedding.weight"], P["out_linear.weight"],
+                            P["out_linear.bias"], pen, toks, lens)
+        return toks, lens
+
+    @staticmethod
+    def _ids_to_reference_lists(toks: torch.Tensor, lens: torch.Tensor) -> List[List[torch.Tensor]]:
+        """Shape the result like the reference: list[B] of list[Tensor]; element 0 is a [1,1] LongTensor holding
+        <sos>, the others are 0-dim int64 tensors (S2VTModel.py:177,220,231-238); eval.py:91 only calls .item()."""
+        host = toks.cpu()
+        n = lens.cpu().tolist()
+        out = []
+        for b in range(host.shape[0]):
+            row = host[b]
+            out.append([row[0:1].view(1, 1)] + [row[j] for j in range(1, n[b])])
+        return out
+
+
+S2VTModel = S2VT   # BASELINE.json's wording; the reference class is S2VTModel.S2VT

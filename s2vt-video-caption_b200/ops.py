@@ -1,0 +1,131 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point).
+
+Every wrapper takes torch CUDA tensors (+ element offsets where a sub-matrix is addressed), checks
+dtype/contiguity, and forwards raw pointers on the current stream.  No arithmetic happens here.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import RowMap, dense, rowmap
+
+
+def _f32(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError("%s must be a contiguous float32 tensor (got %s, contiguous=%s)" % (name, t.dtype, t.is_contiguous()))
+
+
+def gemm_f32(M: int, N: int, K: int, A: torch.Tensor, amap: RowMap, a_trans: bool, B: torch.Tensor, bmap: RowMap,
+             b_trans: bool, C: torch.Tensor, cmap: RowMap, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
+             a_off: int = 0, b_off: int = 0, c_off: int = 0, split_k: int = 1, split_stride: int = 0) -> None:
+    _f32(A, "A"); _f32(B, "B"); _f32(C, "C")
+    L.require_cuda(A, B, C, bias)
+    rc = L.load().s2vt_gemm_f32(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), amap, int(a_trans), L.ptr(B, b_off), bmap,
+                                int(b_trans), L.ptr(C, c_off), cmap, L.ptr(bias), int(accumulate), split_k, split_stride)
+    L.check(rc, "s2vt_gemm_f32")
+
+
+def add_f32(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _f32(a, "a"); _f32(b, "b"); _f32(out, "out")
+    L.require_cuda(a, b, out)
+    L.check(L.load().s2vt_add_f32(L.stream_ptr(a.device), L.ptr(a), L.ptr(b), L.ptr(out), a.numel()), "s2vt_add_f32")
+    return out
+
+
+def lstm_fwd_f32(T: int, B: int, H: int, n_pre: int, pre: Optional[torch.Tensor], bias_sum: torch.Tensor, w_hh: torch.Tensor,
+                 out: torch.Tensor, gates: Optional[torch.Tensor] = None, cells: Optional[torch.Tensor] = None,
+                 h0: Optional[torch.Tensor] = None, c0: Optional[torch.Tensor] = None, hT: Optional[torch.Tensor] = None,
+                 cT: Optional[torch.Tensor] = None, pre_off: int = 0) -> None:
+    _f32(w_hh, "w_hh"); _f32(out, "out")
+    L.require_cuda(w_hh, out)
+    lib = L.load()
+    ws = torch.empty(int(lib.s2vt_lstm_ws_bytes(B, H)), dtype=torch.uint8, device=out.device)
+    rc = lib.s2vt_lstm_fwd_f32(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre, pre_off), L.ptr(bias_sum), L.ptr(w_hh),
+                               L.ptr(h0), L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT), L.ptr(ws))
+    L.check(rc, "s2vt_lstm_fwd_f32")
+
+
+def lstm_bwd_f32(T: int, B: int, H: int, dout_t0: int, dout: Optional[torch.Tensor], gates: torch.Tensor, cells: torch.Tensor,
+                 w_hh: torch.Tensor, dgates: torch.Tensor) -> None:
+    lib = L.load()
+    L.require_cuda(gates, cells, w_hh, dgates)
+    ws = torch.empty(int(lib.s2vt_lstm_ws_bytes(B, H)), dtype=torch.uint8, device=gates.device)
+    rc = lib.s2vt_lstm_bwd_f32(L.stream_ptr(gates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
+                               L.ptr(w_hh), L.ptr(dgates), L.ptr(ws))
+    L.check(rc, "s2vt_lstm_bwd_f32")
+
+
+def embed_gather_f32(table: torch.Tensor, ids: torch.Tensor, ids_off: int, ids_ld: int, B: int, n_t: int, out: torch.Tensor,
+                     out_ld: int, out_off: int = 0) -> None:
+    _f32(table, "table")
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise ValueError("ids must be contiguous int64")
+    L.require_cuda(table, ids, out)
+    rc = L.load().s2vt_embed_gather_f32(L.stream_ptr(out.device), L.ptr(table), table.shape[1], L.ptr(ids, ids_off), ids_ld, B, n_t,
+                                        L.ptr(out, out_off), out_ld)
+    L.check(rc, "s2vt_embed_gather_f32")
+
+
+def embed_scatter_add_f32(grad_table: torch.Tensor, ids: torch.Tensor, ids_off: int, ids_ld: int, B: int, n_t: int,
+                          src: torch.Tensor, src_ld: int, src_off: int = 0) -> None:
+    _f32(grad_table, "grad_table")
+    L.require_cuda(grad_table, ids, src)
+    rc = L.load().s2vt_embed_scatter_add_f32(L.stream_ptr(src.device), L.ptr(grad_table), grad_table.shape[1], L.ptr(ids, ids_off),
+                                             ids_ld, B, n_t, L.ptr(src, src_off), src_ld)
+    L.check(rc, "s2vt_embed_scatter_add_f32")
+
+
+def colsum_f32(X: torch.Tensor, M: int, N: int, ld: int, out: torch.Tensor, accumulate: bool = False, x_off: int = 0) -> None:
+    L.require_cuda(X, out)
+    rc = L.load().s2vt_colsum_f32(L.stream_ptr(X.device), L.ptr(X, x_off), M, N, ld, L.ptr(out), int(accumulate))
+    L.check(rc, "s2vt_colsum_f32")
+
+
+def ce_f32(logits: torch.Tensor, R: int, V: int, targets: torch.Tensor, t_off: int, tmap: RowMap, loss: torch.Tensor,
+           dlogits: Optional[torch.Tensor] = None, gscale: Optional[torch.Tensor] = None) -> None:
+    _f32(logits, "logits")
+    if targets.dtype != torch.int64 or not targets.is_contiguous():
+        raise ValueError("targets must be contiguous int64")
+    L.require_cuda(logits, targets, loss, dlogits, gscale)
+    row_loss = torch.empty(R, dtype=torch.float32, device=logits.device)
+    rc = L.load().s2vt_ce_f32(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
+                              L.ptr(loss), L.ptr(dlogits), L.ptr(gscale))
+    L.check(rc, "s2vt_ce_f32")
+
+
+def adam_f32(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
+             eps: float, step: int, grad_scale: float = 1.0, bf16_copy: Optional[torch.Tensor] = None) -> None:
+    L.require_cuda(p, g, m, v)
+    rc = L.load().s2vt_adam_f32(L.stream_ptr(p.device), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, beta1, beta2, eps,
+                                step, grad_scale, L.ptr(bf16_copy))
+    L.check(rc, "s2vt_adam_f32")
+
+
+def greedy_decode_f32(B: int, H: int, E: int, V: int, n_steps: int, sos_ix: int, pre2_vid: torch.Tensor, pre_off: int,
+                      w_cat: torch.Tensor, emb: torch.Tensor, w_out: torch.Tensor, b_out: torch.Tensor, h2: torch.Tensor,
+                      c2: torch.Tensor, tokens: torch.Tensor) -> None:
+    lib = L.load()
+    L.require_cuda(pre2_vid, w_cat, emb, w_out, b_out, h2, c2, tokens)
+    ws = torch.empty(int(lib.s2vt_greedy_ws_bytes(B, H, E, V)), dtype=torch.uint8, device=h2.device)
+    rc = lib.s2vt_greedy_decode_f32(L.stream_ptr(h2.device), B, H, E, V, n_steps, sos_ix, L.ptr(pre2_vid, pre_off), L.ptr(w_cat),
+                                    L.ptr(emb), L.ptr(w_out), L.ptr(b_out), L.ptr(h2), L.ptr(c2), L.ptr(tokens), L.ptr(ws))
+    L.check(rc, "s2vt_greedy_decode_f32")
+
+
+def beam_search_f32(B: int, H: int, E: int, V: int, beam_width: int, max_depth: int, topk: int, sos_ix: int, eos_ix: int,
+                    state: torch.Tensor, bias1: torch.Tensor, w_hh1: torch.Tensor, w_cat2: torch.Tensor, bias2: torch.Tensor,
+                    emb: torch.Tensor, w_out: torch.Tensor, b_out: torch.Tensor, len_pen: torch.Tensor, out_tokens: torch.Tensor,
+                    out_len: torch.Tensor) -> None:
+    lib = L.load()
+    L.require_cuda(state, bias1, w_hh1, w_cat2, bias2, emb, w_out, b_out, len_pen, out_tokens, out_len)
+    ws = torch.empty(int(lib.s2vt_beam_ws_bytes(B, H, E, V, beam_width, max_depth, topk)), dtype=torch.uint8, device=state.device)
+    rc = lib.s2vt_beam_search_f32(L.stream_ptr(state.device), B, H, E, V, beam_width, max_depth, topk, sos_ix, eos_ix, L.ptr(state),
+                                  L.ptr(bias1), L.ptr(w_hh1), L.ptr(w_cat2), L.ptr(bias2), L.ptr(emb), L.ptr(w_out), L.ptr(b_out),
+                                  L.ptr(len_pen), L.ptr(out_tokens), L.ptr(out_len), L.ptr(ws))
+    L.check(rc, "s2vt_beam_search_f32")
+
+
+__all__ = [n for n in dir() if n.endswith("_f32")] + ["RowMap", "dense", "rowmap"]

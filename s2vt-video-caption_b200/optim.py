@@ -1,0 +1,74 @@
+"""Fused Adam over a flat parameter buffer (train.py:89-93,125: Adam(lr=1e-4), torch defaults)."""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+
+from . import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (no weight decay, no amsgrad) in ONE kernel launch per step.
+
+    On the first step the parameters are re-homed into one contiguous fp32 buffer (param.data become views
+    of it, so state_dict / named_parameters are unchanged); gradients are gathered into a matching flat
+    buffer.  `flat_grad_views()` exposes views that a backward pass (or the data-parallel all-reduce) can
+    write directly, in which case no gather copy happens."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
+        self._flat = None
+
+    def _ensure_flat(self):
+        if self._flat is not None:
+            ps = self._flat["params"]
+            base = self._flat["p"]
+            ok = all(p.data.data_ptr() == base.data_ptr() + o * 4 for p, o in zip(ps, self._flat["offsets"]))
+            if ok:
+                return self._flat
+        ps: List[torch.nn.Parameter] = [p for g in self.param_groups for p in g["params"]]
+        dev = ps[0].device
+        offsets, n = [], 0
+        for p in ps:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FusedAdam needs float32 parameters on one device")
+            offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+        flat = torch.zeros(n, device=dev)
+        old = self._flat
+        for p, o in zip(ps, offsets):
+            v = flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+        g = torch.zeros(n, device=dev)
+        m = torch.zeros(n, device=dev)
+        v2 = torch.zeros(n, device=dev)
+        step = 0
+        if old is not None and old["p"].numel() == n:
+            m.copy_(old["m"]); v2.copy_(old["v"]); step = old["step"]
+        self._flat = dict(params=ps, offsets=offsets, p=flat, g=g, m=m, v=v2, step=step, n=n)
+        return self._flat
+
+    def flat_grad_views(self):
+        f = self._ensure_flat()
+        return [f["g"][o:o + p.numel()].view(p.shape) for p, o in zip(f["params"], f["offsets"])]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        f = self._ensure_flat()
+        for p, o in zip(f["params"], f["offsets"]):
+            gv = f["g"][o:o + p.numel()].view(p.shape)
+            if p.grad is None:
+                gv.zero_()
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)
+        group = self.param_groups[0]
+        f["step"] += 1
+        ops.adam_f32(f["p"], f["g"], f["m"], f["v"], float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
+                     float(group["eps"]), f["step"])
+        return loss

@@ -1,0 +1,167 @@
+"""Unit parity of each CUDA kernel against a plain PyTorch expression (fp64 math on the same inputs).
+All calls go through the C ABI (ctypes).  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import s2vt_b200  # noqa: E402
+from s2vt_b200 import lib as L  # noqa: E402
+from s2vt_b200 import ops  # noqa: E402
+from s2vt_b200.lib import dense, rowmap  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    s2vt_b200.load()
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(1e-30, b.double().abs().max().item())
+
+
+# ------------------------------------------------------------------ fp32 GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 1, 4), (64, 64, 64), (237, 40, 16), (300, 2048, 512), (5, 13000, 512), (513, 130, 1000)])
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_f32(dev, M, N, K, a_trans, b_trans):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    Bm = torch.randn(N, K, generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = (A.double() @ Bm.double().T + bias.double()).float()
+    As = A.T.contiguous() if a_trans else A
+    Bs = Bm.T.contiguous() if b_trans else Bm
+    C = torch.full((M, N), float("nan"), device=dev)
+    ops.gemm_f32(M, N, K, As, dense(M if a_trans else K), a_trans, Bs, dense(N if b_trans else K), b_trans, C, dense(N), bias=bias)
+    assert _rel(C, ref) < 2e-6
+    # accumulate on top
+    ops.gemm_f32(M, N, K, As, dense(M if a_trans else K), a_trans, Bs, dense(N if b_trans else K), b_trans, C, dense(N), accumulate=True)
+    ref2 = (2 * (A.double() @ Bm.double().T) + bias.double()).float()
+    assert _rel(C, ref2) < 2e-6
+
+
+def test_gemm_f32_rowmaps_and_splitk(dev):
+    B_, L_, F_, H_ = 5, 7, 24, 16
+    g = torch.Generator().manual_seed(3)
+    feats = torch.randn(B_, L_, F_, generator=g).to(dev)
+    W = torch.randn(H_, F_, generator=g).to(dev)
+    out = torch.empty(L_ * B_, H_, device=dev)
+    ops.gemm_f32(L_ * B_, H_, F_, feats, rowmap(B_, F_, L_ * F_), False, W, dense(F_), False, out, dense(H_))
+    ref = (feats.double() @ W.double().T).transpose(0, 1).reshape(L_ * B_, H_).float()
+    assert _rel(out, ref) < 2e-6
+    # write time-major rows into a batch-major output
+    out_bm = torch.empty(B_, L_, H_, device=dev)
+    ops.gemm_f32(L_ * B_, H_, F_, feats, rowmap(B_, F_, L_ * F_), False, W, dense(F_), False, out_bm, rowmap(B_, H_, L_ * H_))
+    assert _rel(out_bm, (feats.double() @ W.double().T).float()) < 2e-6
+    # split-K partial planes sum to the product
+    M, N, K, S = 33, 70, 512, 4
+    A = torch.randn(M, K, generator=g).to(dev); Bm = torch.randn(N, K, generator=g).to(dev)
+    part = torch.zeros(S, M, N, device=dev)
+    ops.gemm_f32(M, N, K, A, dense(K), False, Bm, dense(K), False, part, dense(N), split_k=S, split_stride=M * N)
+    assert _rel(part.sum(0), (A.double() @ Bm.double().T).float()) < 2e-6
+
+
+# ------------------------------------------------------------------ bf16 tcgen05 GEMM
+def _gemm_bf16(dev, M, N, K, a_mn, b_mn, out_bf16=False, bias=True, accumulate=False, seed=0):
+    g = torch.Generator().manual_seed(seed + M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    Bm = torch.randn(N, K, generator=g).to(dev).bfloat16()
+    bv = torch.randn(N, generator=g).to(dev) if bias else None
+    ref = A.double() @ Bm.double().T
+    if bias:
+        ref = ref + bv.double()
+    As = A.T.contiguous() if a_mn else A
+    Bs = Bm.T.contiguous() if b_mn else Bm
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    C = C0.clone() if not out_bf16 else torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    if accumulate:
+        ref = ref + C0.double()
+    rc = L.load().s2vt_gemm_bf16(L.stream_ptr(dev), M, N, K, L.ptr(As), (M if a_mn else K), int(a_mn), L.ptr(Bs), (N if b_mn else K),
+                                 int(b_mn), L.ptr(C), dense(N), int(out_bf16), L.ptr(bv), int(accumulate))
+    L.check(rc, "s2vt_gemm_bf16")
+    flag = L.load().s2vt_device_error_flag(L.stream_ptr(dev))
+    assert flag == 0, "device error flag %d" % flag
+    return C, ref
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 4096), (5120, 512, 4096), (200, 136, 72), (5056, 13000, 512)])
+def test_gemm_bf16_kmajor(dev, M, N, K):
+    C, ref = _gemm_bf16(dev, M, N, K, False, False)
+    err = (C.double() - ref).abs().max().item()
+    assert err < 2e-3 * (K ** 0.5), err          # exact products, fp32 accumulation: error ~ 1e-6 * sqrt(K) * |terms|
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (2048, 512, 10176), (520, 264, 200)])
+def test_gemm_bf16_mn_major(dev, M, N, K, a_mn, b_mn):
+    C, ref = _gemm_bf16(dev, M, N, K, a_mn, b_mn)
+    err = (C.double() - ref).abs().max().item()
+    assert err < 2e-3 * (K ** 0.5), err
+
+
+def test_gemm_bf16_epilogues(dev):
+    C, ref = _gemm_bf16(dev, 300, 200, 256, False, False, out_bf16=True)
+    assert (C.double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+    C, ref = _gemm_bf16(dev, 300, 200, 256, False, False, bias=False, accumulate=True)
+    assert (C.double() - ref).abs().max().item() < 2e-3 * 16
+
+
+# ------------------------------------------------------------------ small kernels
+def test_ce_and_colsum_and_embed(dev):
+    g = torch.Generator().manual_seed(5)
+    R, V = 37, 1300
+    z = (torch.randn(R, V, generator=g) * 3).to(dev)
+    t = torch.randint(0, V, (R,), generator=g).to(dev)
+    loss = torch.empty((), device=dev)
+    dl = torch.empty_like(z)
+    gs = torch.tensor(0.5, device=dev)
+    ops.ce_f32(z, R, V, t, 0, dense(1), loss, dlogits=dl, gscale=gs)
+    zr = z.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(zr, t)
+    (ref * 0.5).backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert (dl.double() - zr.grad).abs().max().item() < 1e-7
+    cs = torch.empty(V, device=dev)
+    ops.colsum_f32(z, R, V, V, cs)
+    assert _rel(cs, z.double().sum(0).float()) < 1e-5
+    E, Bn, nt = 12, 3, 5
+    tab = torch.randn(50, E, generator=g).to(dev)
+    ids = torch.randint(0, 50, (Bn, nt + 1), generator=g).to(dev)
+    out = torch.empty(nt * Bn, E, device=dev)
+    ops.embed_gather_f32(tab, ids, 0, nt + 1, Bn, nt, out, E)
+    assert torch.equal(out.view(nt, Bn, E), tab[ids[:, :nt]].transpose(0, 1))
+    gt = torch.zeros(50, E, device=dev)
+    ops.embed_scatter_add_f32(gt, ids, 0, nt + 1, Bn, nt, out, E)
+    ref_g = torch.zeros(50, E, device=dev, dtype=torch.float64)
+    ref_g.index_add_(0, ids[:, :nt].T.reshape(-1), out.double())
+    assert _rel(gt, ref_g.float()) < 1e-6
+
+
+def test_adam_matches_torch(dev):
+    g = torch.Generator().manual_seed(9)
+    p0 = torch.randn(1001, generator=g).to(dev)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-4)
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 4):
+        gr = torch.randn(1001, generator=g).to(dev)
+        ref_p.grad = gr.clone()
+        opt.step()
+        ops.adam_f32(p, gr, m, v, 1e-4, 0.9, 0.999, 1e-8, step)
+        assert (p - ref_p.data).abs().max().item() < 1e-7
+
+
+def test_cast_bf16(dev):
+    x = torch.randn(70, 130, device=dev)
+    d = torch.empty(70, 130, dtype=torch.bfloat16, device=dev)
+    dt = torch.empty(130, 70, dtype=torch.bfloat16, device=dev)
+    rc = L.load().s2vt_cast_bf16(L.stream_ptr(dev), L.ptr(x), L.ptr(d), L.ptr(dt), 70, 130)
+    L.check(rc, "cast")
+    assert torch.equal(d, x.bfloat16()) and torch.equal(dt, x.bfloat16().T.contiguous())
+    d2 = torch.empty(70 * 130, dtype=torch.bfloat16, device=dev)
+    L.check(L.load().s2vt_cast_bf16(L.stream_ptr(dev), L.ptr(x), L.ptr(d2), None, 70, 130), "cast")
+    assert torch.equal(d2.view(70, 130), x.bfloat16())
