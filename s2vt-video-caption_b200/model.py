@@ -146,17 +146,28 @@ def train_forward_f32(P: Dict[str, torch.Tensor], feats: torch.Tensor, targets: 
     return logits, saved
 
 
-def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_major: bool, need_dfeats: bool):
+def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_major: bool, need_dfeats: bool,
+                       gout: Optional[Dict[str, torch.Tensor]] = None, on_ready=None):
     """BPTT for train_forward_f32: dl = dL/dlogits ([B,L-1,V] batch-major or [(L-1)B,V] time-major).
-    Returns grads in PARAM_ORDER (+ dfeats or None)."""
+    Returns grads in PARAM_ORDER (+ dfeats or None).  `gout` (name -> preallocated tensor) makes the kernels write
+    straight into e.g. the optimizer's flat gradient buffer; `on_ready(bucket)` is called as soon as all kernels
+    producing a bucket of dp.BUCKETS have been enqueued (the data-parallel all-reduce hooks in here)."""
     B, L, F, H, E, V, T = saved["dims"]
     dev = dl.device
     R = (L - 1) * B
     out1, out2 = saved["out1"], saved["out2"]
     G = {}
+
+    def _new(name, *shape):
+        return gout[name] if gout is not None else torch.empty(*shape, device=dev)
+
+    def _ready(bucket):
+        if on_ready is not None:
+            on_ready(bucket)
+
     hdec_off = L * B * H
     # ---- out_linear
-    gW = torch.empty(V, H, device=dev)
+    gW = _new("out_linear.weight", V, H)
     if dl_batch_major:
         # K runs over batch-major rows k = b*(L-1)+t; the matching h row is (L+t)*B + b
         ops.gemm_f32(V, H, R, dl, dense(V), True, out2, rowmap(L - 1, H, B * H), True, gW, dense(H), b_off=hdec_off)
@@ -165,56 +176,66 @@ def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_majo
         ops.gemm_f32(V, H, R, dl, dense(V), True, out2, dense(H), True, gW, dense(H), b_off=hdec_off)
         amap_rows = dense(V)
     G["out_linear.weight"] = gW
-    gb = torch.empty(V, device=dev)
+    gb = _new("out_linear.bias", V)
     ops.colsum_f32(dl, R, V, V, gb)
     G["out_linear.bias"] = gb
+    _ready("out_linear")
     dout2 = torch.empty(T * B, H, device=dev)          # rows < L*B are never read (dout_t0 = L)
     ops.gemm_f32(R, H, V, dl, amap_rows, False, P["out_linear.weight"], dense(H), True, dout2, dense(H), c_off=hdec_off)
     # ---- word_rnn
     dg2 = torch.empty(T * B, 4 * H, device=dev)
     ops.lstm_bwd_f32(T, B, H, L, dout2, saved["g2"], saved["c2"], P["word_rnn.weight_hh_l0"], dg2)
-    gWih2 = torch.empty(4 * H, E + H, device=dev)
+    gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
     ops.gemm_f32(4 * H, H, T * B, dg2, dense(4 * H), True, out1, dense(H), True, gWih2, dense(E + H), c_off=E)
     ops.gemm_f32(4 * H, E, R, dg2, dense(4 * H), True, saved["emb_seq"], dense(E), True, gWih2, dense(E + H), a_off=L * B * 4 * H)
     G["word_rnn.weight_ih_l0"] = gWih2
-    gWhh2 = torch.empty(4 * H, H, device=dev)
+    gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
     ops.gemm_f32(4 * H, H, (T - 1) * B, dg2, dense(4 * H), True, out2, dense(H), True, gWhh2, dense(H), a_off=B * 4 * H)
     G["word_rnn.weight_hh_l0"] = gWhh2
-    gb2 = torch.empty(4 * H, device=dev)
+    gb2 = _new("word_rnn.bias_ih_l0", 4 * H)
     ops.colsum_f32(dg2, T * B, 4 * H, 4 * H, gb2)
     G["word_rnn.bias_ih_l0"] = gb2
-    G["word_rnn.bias_hh_l0"] = gb2.clone()
+    gb2b = _new("word_rnn.bias_hh_l0", 4 * H)
+    ops.colsum_f32(dg2, T * B, 4 * H, 4 * H, gb2b)
+    G["word_rnn.bias_hh_l0"] = gb2b
+    _ready("word_rnn")
     # d input2 = dg2 . W_ih2: vid half -> dL/d output1, embedding half -> dense embedding grad
     dout1 = torch.empty(T * B, H, device=dev)
     ops.gemm_f32(T * B, H, 4 * H, dg2, dense(4 * H), False, P["word_rnn.weight_ih_l0"], dense(E + H), True, dout1, dense(H), b_off=E)
     demb = torch.empty(R, E, device=dev)
     ops.gemm_f32(R, E, 4 * H, dg2, dense(4 * H), False, P["word_rnn.weight_ih_l0"], dense(E + H), True, demb, dense(E),
                  a_off=L * B * 4 * H)
-    gE = torch.zeros(V, E, device=dev)
+    gE = _new("embedding.weight", V, E)
+    gE.zero_()
     ops.embed_scatter_add_f32(gE, targets, 0, L - 1, B, L - 1, demb, E)
     G["embedding.weight"] = gE
+    _ready("embedding")
     # ---- vid_rnn
     dg1 = torch.empty(T * B, 4 * H, device=dev)
     ops.lstm_bwd_f32(T, B, H, 0, dout1, saved["g1"], saved["c1"], P["vid_rnn.weight_hh_l0"], dg1)
-    gWih1 = torch.empty(4 * H, H, device=dev)
+    gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
     ops.gemm_f32(4 * H, H, L * B, dg1, dense(4 * H), True, saved["xproj"], dense(H), True, gWih1, dense(H))
     G["vid_rnn.weight_ih_l0"] = gWih1
-    gWhh1 = torch.empty(4 * H, H, device=dev)
+    gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)
     ops.gemm_f32(4 * H, H, (T - 1) * B, dg1, dense(4 * H), True, out1, dense(H), True, gWhh1, dense(H), a_off=B * 4 * H)
     G["vid_rnn.weight_hh_l0"] = gWhh1
-    gb1 = torch.empty(4 * H, device=dev)
+    gb1 = _new("vid_rnn.bias_ih_l0", 4 * H)
     ops.colsum_f32(dg1, T * B, 4 * H, 4 * H, gb1)
     G["vid_rnn.bias_ih_l0"] = gb1
-    G["vid_rnn.bias_hh_l0"] = gb1.clone()
+    gb1b = _new("vid_rnn.bias_hh_l0", 4 * H)
+    ops.colsum_f32(dg1, T * B, 4 * H, 4 * H, gb1b)
+    G["vid_rnn.bias_hh_l0"] = gb1b
+    _ready("vid_rnn")
     # ---- feat_linear
     dxp = torch.empty(L * B, H, device=dev)
     ops.gemm_f32(L * B, H, 4 * H, dg1, dense(4 * H), False, P["vid_rnn.weight_ih_l0"], dense(H), True, dxp, dense(H))
-    gWf = torch.empty(H, F, device=dev)
+    gWf = _new("feat_linear.weight", H, F)
     ops.gemm_f32(H, F, L * B, dxp, dense(H), True, feats, rowmap(B, F, L * F), True, gWf, dense(F))
     G["feat_linear.weight"] = gWf
-    gbf = torch.empty(H, device=dev)
+    gbf = _new("feat_linear.bias", H)
     ops.colsum_f32(dxp, L * B, H, H, gbf)
     G["feat_linear.bias"] = gbf
+    _ready("feat_linear")
     dfeats = None
     if need_dfeats:                                     # dataloader.py:38 makes feats require grad
         dfeats = torch.empty(B, L, F, device=dev)
@@ -222,31 +243,57 @@ def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_majo
     return [G[k] for k in PARAM_ORDER], dfeats
 
 
+def _direct_grad_targets(module):
+    """When an optimizer attached its flat gradient buffer (FusedAdam.attach) and no gradient is pending, backward
+    writes into those views and installs them as p.grad itself (autograd then has nothing to accumulate)."""
+    views = getattr(module, "_grad_views", None)
+    if views is None:
+        return None, None
+    params = dict(module.named_parameters())
+    for k in PARAM_ORDER:
+        p = params[k]
+        if p.grad is not None or views[k].device != p.device or not p.requires_grad:
+            return None, None
+    return views, getattr(module, "_on_bucket_ready", None)
+
+
+def _finish_grads(module, direct, grads):
+    if direct is None:
+        return tuple(grads)
+    params = dict(module.named_parameters())
+    for k in PARAM_ORDER:
+        params[k].grad = direct[k]
+    return (None,) * len(PARAM_ORDER)
+
+
 class _TrainLogitsFn(torch.autograd.Function):
     """forward(mode='train') -> materialised fp32 logits [B,L-1,V], differentiable (train.py:120-124)."""
 
     @staticmethod
-    def forward(ctx, feats, targets, *params):
+    def forward(ctx, module, feats, targets, *params):
         P = dict(zip(PARAM_ORDER, params))
         need = any(ctx.needs_input_grad)
         logits, saved = train_forward_f32(P, feats, targets, stash=need, batch_major_logits=True)
-        ctx.saved, ctx.P, ctx.feats, ctx.targets = saved, P, feats, targets
+        ctx.saved, ctx.P, ctx.feats, ctx.targets, ctx.module = saved, P, feats, targets, module
         return logits
 
     @staticmethod
     def backward(ctx, dl):
         dl = dl.contiguous()
-        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.targets, dl, True, ctx.needs_input_grad[0])
+        direct, cb = _direct_grad_targets(ctx.module)
+        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.targets, dl, True, ctx.needs_input_grad[1],
+                                           gout=direct, on_ready=cb)
         ctx.saved = None
-        return (dfeats, None) + tuple(grads)
+        return (None, dfeats, None) + _finish_grads(ctx.module, direct, grads)
 
 
 class _TrainLossFn(torch.autograd.Function):
     """Fused forward + MaskCriterion (utils.py:13-26) without handing the logits to autograd."""
 
     @staticmethod
-    def forward(ctx, feats, targets_full, *params):
+    def forward(ctx, module, feats, targets_full, *params):
         P = dict(zip(PARAM_ORDER, params))
+        ctx.module = module
         B, L, _ = feats.shape
         V = P["embedding.weight"].shape[0]
         need = any(ctx.needs_input_grad)
@@ -266,9 +313,11 @@ class _TrainLossFn(torch.autograd.Function):
         scratch = torch.empty((), device=logits.device)
         g = gloss.contiguous().to(torch.float32)
         ops.ce_f32(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), scratch, dlogits=logits, gscale=g)
-        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.tin, logits, False, ctx.needs_input_grad[0])
+        direct, cb = _direct_grad_targets(ctx.module)
+        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.tin, logits, False, ctx.needs_input_grad[1],
+                                           gout=direct, on_ready=cb)
         ctx.saved = ctx.logits = None
-        return (dfeats, None) + tuple(grads)
+        return (None, dfeats, None) + _finish_grads(ctx.module, direct, grads)
 
 
 # --------------------------------------------------------------------------- the module
@@ -300,6 +349,8 @@ class S2VT(nn.Module):
         self.train_precision = train_precision
         self.decode_precision = decode_precision
         self.beam_topk = 20                     # S2VTModel.py:216
+        self._grad_views = None                 # set by FusedAdam.attach(): backward writes gradients in place
+        self._on_bucket_ready = None
 
     # ---- helpers
     def _params(self) -> Dict[str, torch.Tensor]:
@@ -332,7 +383,7 @@ class S2VT(nn.Module):
                                    "(S2VTModel.py:73-75)" % (feats.shape[0], self.length - 1, tuple(targets.shape)))
             targets = targets.contiguous().to(torch.int64)
             P = self._params()
-            return _TrainLogitsFn.apply(feats, targets, *[P[k] for k in PARAM_ORDER])
+            return _TrainLogitsFn.apply(self, feats, targets, *[P[k] for k in PARAM_ORDER])
         elif mode == 'test':
             with torch.no_grad():
                 return self._greedy(feats.detach())
@@ -351,7 +402,7 @@ class S2VT(nn.Module):
         if targets.dim() != 2 or targets.shape[1] != self.length:
             raise RuntimeError("targets must be [B, length] (got %s)" % (tuple(targets.shape),))
         P = self._params()
-        return _TrainLossFn.apply(feats.contiguous(), targets.contiguous().to(torch.int64), *[P[k] for k in PARAM_ORDER])
+        return _TrainLossFn.apply(self, feats.contiguous(), targets.contiguous().to(torch.int64), *[P[k] for k in PARAM_ORDER])
 
     # ---- greedy (S2VTModel.py:82-110)
     def _greedy(self, feats):

@@ -13,6 +13,52 @@ from . import lib as L
 from .lib import RowMap, dense, rowmap
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Optional per-call timing (bench.py's roofline leg): CUDA events on the launching stream around each C call.
+_PROFILE = None
+
+
+class profile:
+    """with ops.profile() as prof: ...   ->  prof.summary() = {tag: (calls, total_ms, flops, bytes)} after a sync."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, e0, e1, flops, nbytes in self.records:
+            c, ms, f, b = out.get(tag, (0, 0.0, 0.0, 0.0))
+            out[tag] = (c + 1, ms + e0.elapsed_time(e1), f + flops, b + nbytes)
+        return out
+
+
+class _timed:
+    def __init__(self, tag, flops=0.0, nbytes=0.0):
+        self.tag, self.flops, self.nbytes = tag, flops, nbytes
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            _PROFILE.records.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))
+
+
 def _f32(t: torch.Tensor, name: str) -> None:
     if t.dtype != torch.float32 or not t.is_contiguous():
         raise ValueError("%s must be a contiguous float32 tensor (got %s, contiguous=%s)" % (name, t.dtype, t.is_contiguous()))
@@ -23,8 +69,9 @@ def gemm_f32(M: int, N: int, K: int, A: torch.Tensor, amap: RowMap, a_trans: boo
              a_off: int = 0, b_off: int = 0, c_off: int = 0, split_k: int = 1, split_stride: int = 0) -> None:
     _f32(A, "A"); _f32(B, "B"); _f32(C, "C")
     L.require_cuda(A, B, C, bias)
-    rc = L.load().s2vt_gemm_f32(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), amap, int(a_trans), L.ptr(B, b_off), bmap,
-                                int(b_trans), L.ptr(C, c_off), cmap, L.ptr(bias), int(accumulate), split_k, split_stride)
+    with _timed("gemm_f32", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+        rc = L.load().s2vt_gemm_f32(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), amap, int(a_trans), L.ptr(B, b_off), bmap,
+                                    int(b_trans), L.ptr(C, c_off), cmap, L.ptr(bias), int(accumulate), split_k, split_stride)
     L.check(rc, "s2vt_gemm_f32")
 
 
@@ -43,8 +90,9 @@ def lstm_fwd_f32(T: int, B: int, H: int, n_pre: int, pre: Optional[torch.Tensor]
     L.require_cuda(w_hh, out)
     lib = L.load()
     ws = torch.empty(int(lib.s2vt_lstm_ws_bytes(B, H)), dtype=torch.uint8, device=out.device)
-    rc = lib.s2vt_lstm_fwd_f32(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre, pre_off), L.ptr(bias_sum), L.ptr(w_hh),
-                               L.ptr(h0), L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT), L.ptr(ws))
+    with _timed("lstm_fwd_f32", 2.0 * T * B * H * 4 * H, 4.0 * T * (4 * H * H + B * 10 * H)):
+        rc = lib.s2vt_lstm_fwd_f32(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre, pre_off), L.ptr(bias_sum), L.ptr(w_hh),
+                                   L.ptr(h0), L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT), L.ptr(ws))
     L.check(rc, "s2vt_lstm_fwd_f32")
 
 
@@ -53,8 +101,9 @@ def lstm_bwd_f32(T: int, B: int, H: int, dout_t0: int, dout: Optional[torch.Tens
     lib = L.load()
     L.require_cuda(gates, cells, w_hh, dgates)
     ws = torch.empty(int(lib.s2vt_lstm_ws_bytes(B, H)), dtype=torch.uint8, device=gates.device)
-    rc = lib.s2vt_lstm_bwd_f32(L.stream_ptr(gates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
-                               L.ptr(w_hh), L.ptr(dgates), L.ptr(ws))
+    with _timed("lstm_bwd_f32", 2.0 * T * B * H * 4 * H, 4.0 * T * (4 * H * H + B * 11 * H)):
+        rc = lib.s2vt_lstm_bwd_f32(L.stream_ptr(gates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
+                                   L.ptr(w_hh), L.ptr(dgates), L.ptr(ws))
     L.check(rc, "s2vt_lstm_bwd_f32")
 
 
@@ -91,16 +140,18 @@ def ce_f32(logits: torch.Tensor, R: int, V: int, targets: torch.Tensor, t_off: i
         raise ValueError("targets must be contiguous int64")
     L.require_cuda(logits, targets, loss, dlogits, gscale)
     row_loss = torch.empty(R, dtype=torch.float32, device=logits.device)
-    rc = L.load().s2vt_ce_f32(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
-                              L.ptr(loss), L.ptr(dlogits), L.ptr(gscale))
+    with _timed("ce_f32", 0.0, 4.0 * R * V * (2 if dlogits is not None else 1)):
+        rc = L.load().s2vt_ce_f32(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
+                                  L.ptr(loss), L.ptr(dlogits), L.ptr(gscale))
     L.check(rc, "s2vt_ce_f32")
 
 
 def adam_f32(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
              eps: float, step: int, grad_scale: float = 1.0, bf16_copy: Optional[torch.Tensor] = None) -> None:
     L.require_cuda(p, g, m, v)
-    rc = L.load().s2vt_adam_f32(L.stream_ptr(p.device), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, beta1, beta2, eps,
-                                step, grad_scale, L.ptr(bf16_copy))
+    with _timed("adam_f32", 0.0, 28.0 * p.numel()):
+        rc = L.load().s2vt_adam_f32(L.stream_ptr(p.device), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, beta1, beta2, eps,
+                                    step, grad_scale, L.ptr(bf16_copy))
     L.check(rc, "s2vt_adam_f32")
 
 

@@ -1,7 +1,7 @@
 """Fused Adam over a flat parameter buffer (train.py:89-93,125: Adam(lr=1e-4), torch defaults)."""
 from __future__ import annotations
 
-from typing import Iterable, List
+from typing import Callable, Iterable, List, Optional
 
 import torch
 
@@ -11,10 +11,10 @@ from . import ops
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (no weight decay, no amsgrad) in ONE kernel launch per step.
 
-    On the first step the parameters are re-homed into one contiguous fp32 buffer (param.data become views
-    of it, so state_dict / named_parameters are unchanged); gradients are gathered into a matching flat
-    buffer.  `flat_grad_views()` exposes views that a backward pass (or the data-parallel all-reduce) can
-    write directly, in which case no gather copy happens."""
+    On first use the parameters are re-homed into one contiguous fp32 buffer (param.data become views of it, so
+    state_dict / named_parameters are unchanged) with a matching flat gradient buffer.  `attach(model)` lets the
+    model's backward write gradients straight into that buffer (p.grad become views of it): no gather copy, and
+    the data-parallel all-reduce works on contiguous bucket slices."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
         super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
@@ -22,10 +22,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _ensure_flat(self):
         if self._flat is not None:
-            ps = self._flat["params"]
             base = self._flat["p"]
-            ok = all(p.data.data_ptr() == base.data_ptr() + o * 4 for p, o in zip(ps, self._flat["offsets"]))
-            if ok:
+            if all(p.data.data_ptr() == base.data_ptr() + o * 4 for p, o in zip(self._flat["params"], self._flat["offsets"])):
                 return self._flat
         ps: List[torch.nn.Parameter] = [p for g in self.param_groups for p in g["params"]]
         dev = ps[0].device
@@ -54,8 +52,19 @@ class FusedAdam(torch.optim.Optimizer):
         f = self._ensure_flat()
         return [f["g"][o:o + p.numel()].view(p.shape) for p, o in zip(f["params"], f["offsets"])]
 
+    def attach(self, model, on_bucket_ready: Optional[Callable[[str], None]] = None) -> None:
+        """Let `model`'s backward write its gradients directly into this optimizer's flat buffer."""
+        views = self.flat_grad_views()
+        names = [n for n, _ in model.named_parameters()]
+        params = [p for _, p in model.named_parameters()]
+        f = self._flat
+        if len(params) != len(f["params"]) or any(a is not b for a, b in zip(params, f["params"])):
+            raise ValueError("attach(): the optimizer must have been built from model.parameters()")
+        model._grad_views = dict(zip(names, views))
+        model._on_bucket_ready = on_bucket_ready
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, grad_scale: float = 1.0):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -70,5 +79,5 @@ class FusedAdam(torch.optim.Optimizer):
         group = self.param_groups[0]
         f["step"] += 1
         ops.adam_f32(f["p"], f["g"], f["m"], f["v"], float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
-                     float(group["eps"]), f["step"])
+                     float(group["eps"]), f["step"], grad_scale=grad_scale)
         return loss

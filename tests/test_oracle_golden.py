@@ -112,3 +112,25 @@ def test_targets_shape_error():
     P, feats, targets, mask, c = golden_inputs(g)
     with pytest.raises(ValueError):
         O.forward_train(P, feats, targets)        # [B,L] instead of [B,L-1]
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_torch_port_matches_golden(name):
+    """The CPU-baseline port (oracle/torch_port.py) reproduces the reference's logits, loss, grads and greedy ids."""
+    import torch
+    from oracle.torch_port import S2VTCpuPort
+    g = load_golden(name)
+    P, feats, targets, mask, c = golden_inputs(g)
+    m = S2VTCpuPort(c["V"], c["F"], c["L"], c["H"], c["E"])
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in P.items()}, strict=True)
+    tf = torch.from_numpy(feats).requires_grad_(True)
+    tt, tm = torch.from_numpy(targets), torch.from_numpy(mask)
+    logits = m.train_logits(tf, tt[:, :-1])
+    loss = m.criterion(logits, tt, tm)
+    loss.backward()
+    assert np.abs(logits.detach().numpy() - g["logits"]).max() <= 2e-5 * max(1.0, np.abs(g["logits"]).max())
+    assert abs(loss.item() - g["loss"]) <= 1e-5 * abs(g["loss"])
+    for k, p in m.named_parameters():
+        ref = g["grad/" + k]
+        assert np.abs(p.grad.numpy() - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k
+    assert np.array_equal(m.greedy(tf.detach()).numpy(), g["greedy"])
