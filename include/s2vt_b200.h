@@ -96,6 +96,16 @@ int s2vt_lstm_fwd_f32(void* stream, int T, int B, int H, int n_pre,
                       const float* h0, const float* c0,
                       float* out, float* gates, float* cells, float* hT, float* cT, void* ws);
 
+/* Same recurrence on the tensor cores: a persistent thread-block cluster (H/32 CTAs, 16 batch columns per cluster)
+ * keeps the bf16 W_hh slices resident in shared memory for all T steps, multiplies with tcgen05.mma into TMEM and
+ * exchanges h_t between CTAs through distributed shared memory.  Needs H % 64 == 0, 64 <= H <= 512.
+ *   w_hh_bf16 [4H,H] bf16;  pre / bias_sum / h0 / c0 / hT / cT as above (fp32)
+ *   out_bf16 [T,B,H] bf16;  gates_bf16 [T,B,4H] bf16 or NULL;  cells [T,B,H] f32 or NULL */
+int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
+                       const float* pre, const float* bias_sum, const void* w_hh_bf16,
+                       const float* h0, const float* c0,
+                       void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT);
+
 /* BPTT through one layer from a zero final-state gradient.
  *   dout   [T, B, H]  dL/dh_t from above; rows t < dout_t0 are treated as zero (and not read)
  *   gates, cells      the forward stash;  c0 = 0 is assumed (the reference never passes a state in training)

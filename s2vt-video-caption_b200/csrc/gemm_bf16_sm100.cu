@@ -9,10 +9,9 @@
 // or MN-major ([K, rows], used by the weight-gradient products where the reduction runs over time x batch).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "sm100_err.cuh"
 
 namespace s2vt {
-
-__device__ int g_sm100_error = 0;   // set when an mbarrier wait times out (never expected)
 
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -210,11 +209,12 @@ using namespace s2vt;
 
 extern "C" int s2vt_has_tcgen05(void) { return 1; }
 
+namespace s2vt { int lstm_bf16_error_flag(); }
+
 extern "C" int s2vt_device_error_flag(void* stream) {
-  int v = -1;
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -2;
-  if (cudaMemcpyFromSymbol(&v, g_sm100_error, sizeof(int)) != cudaSuccess) return -3;
-  return v;
+  const int a = read_sm100_error_flag(), b = lstm_bf16_error_flag();
+  return a != 0 ? a : b;
 }
 
 extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,

@@ -45,10 +45,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a lost arrival must not hang the GPU box (a hang is a strike).  Returns false on timeout.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin)
-    if (mbar_try_wait(bar, parity)) return true;
-  return false;
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int spin = 0; spin < 64; ++spin)
+      if (mbar_try_wait(bar, parity)) return true;
+    if (globaltimer_ns() - t0 > 2000000000ull) return false;      // 2 s: far beyond any legitimate wait
+  }
 }
 
 // ------------------------------------------------------------------ TMA
