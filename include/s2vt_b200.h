@@ -100,7 +100,12 @@ int s2vt_lstm_fwd_f32(void* stream, int T, int B, int H, int n_pre,
  * keeps the bf16 W_hh slices resident in shared memory for all T steps, multiplies with tcgen05.mma into TMEM and
  * exchanges h_t between CTAs through distributed shared memory.  Needs H % 64 == 0, 64 <= H <= 512.
  *   w_hh_bf16 [4H,H] bf16;  pre / bias_sum / h0 / c0 / hT / cT as above (fp32)
- *   out_bf16 [T,B,H] bf16;  gates_bf16 [T,B,4H] bf16 or NULL;  cells [T,B,H] f32 or NULL */
+ *   out_bf16 [T,B,H] bf16 (time-major, feeds the next GEMM)
+ *   gates_bf16 / cells: BPTT stash in a kernel-private layout shared only with s2vt_lstm_bwd_bf16, or NULL.
+ *     With Bp = s2vt_lstm_bf16_batch_pad(B), nbt = Bp/16, CS = H/32:
+ *       gates_bf16 [T][nbt][CS][16][32][4] bf16  (T*Bp*4H elements; innermost = i,f,g,o of one unit)
+ *       cells      [T][nbt][CS][16][32]    f32   (T*Bp*H elements) */
+int64_t s2vt_lstm_bf16_batch_pad(int B);
 int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
                        const float* pre, const float* bias_sum, const void* w_hh_bf16,
                        const float* h0, const float* c0,

@@ -2,19 +2,21 @@
 // timesteps without leaving the chip.
 //
 //   cluster = H/32 CTAs (16 for H = 512); CTA c owns hidden units [32c, 32c+32) = 128 gate rows (i,f,g,o x 32)
-//   W_hh slice  [128 rows x H] bf16 : loaded ONCE by TMA (128B swizzle), resident in shared memory for all T steps
-//   h_{t-1}^T   [NB batch x H] bf16 : double-buffered in shared memory in the canonical no-swizzle K-major layout
-//   per step:   gates[128 x NB] = W_slice . h_{t-1}^T      tcgen05.mma M=128 N=NB K=16, fp32 accumulator in TMEM
-//               epilogue warps: tcgen05.ld -> + input-side pre-activation (prefetched from HBM/L2) -> sigmoid/tanh
-//               -> gate exchange through 8 KB of smem -> c,h update (c stays in registers for the whole sequence)
-//               -> the CTA's 32 x NB slice of h_t is pushed to ALL cluster peers with cp.async.bulk (DSMEM),
-//                  completing on each peer's mbarrier: the only inter-CTA synchronisation per step.
+//   W_hh slice  [128 rows x H] bf16 : loaded ONCE into TENSOR MEMORY (tcgen05.st, 128 lanes x H/2 columns) and used as the
+//                                     A operand of every step's MMAs -- the weights never touch shared memory again
+//   h_{t-1}^T   [NB batch x H] bf16 : double-buffered in shared memory in the canonical no-swizzle K-major layout (B operand)
+//   per step:   gates[128 x NB] = W_slice . h_{t-1}^T      tcgen05.mma (A in TMEM) M=128 N=NB K=16, fp32 accumulator in TMEM
+//               epilogue warps: tcgen05.ld -> + input-side pre-activation (prefetched one step ahead) -> one MUFU.TANH per gate
+//               -> gate exchange through smem -> c,h update (c stays in registers for the whole sequence)
+//               -> each warp pushes its 16-byte chunks of h_t straight from registers into the h buffer of EVERY cluster
+//                  peer with st.async (DSMEM), completing on the peer's mbarrier: the only inter-CTA sync per step.
 //
 // There is no grid-wide barrier and no global-memory round trip on the recurrent critical path; the stash for BPTT
-// (post-activation gates bf16, cell state fp32, h bf16) streams to HBM off the critical path.
+// (post-activation gates bf16, cell state fp32) streams to HBM in a kernel-private, fully coalesced layout.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "sm100_err.cuh"
+#include <string.h>
 
 namespace s2vt {
 
@@ -30,10 +32,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank));
   return r;
 }
-// local smem -> peer smem bulk copy; completes (complete_tx) on the PEER's mbarrier
-__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_local, uint32_t bytes, uint32_t bar_cluster) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_cluster), "r"(src_local), "r"(bytes), "r"(bar_cluster) : "memory");
+// 16 bytes from registers into a PEER's shared memory; completes (complete_tx 16) on the peer's mbarrier
+__device__ __forceinline__ void st_async_16(uint32_t dst_cluster, uint4 v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // generic smem descriptor: layout_type 0 = no swizzle (core matrices of 8 rows x 16 B), 2 = 128B swizzle
@@ -46,56 +48,94 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
   d |= (uint64_t)layout_type << 61;
   return d;
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one MUFU op per activation: tanh.approx.f32 (max rel. error ~2^-11, below bf16 resolution);
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5
 __device__ __forceinline__ float fast_tanh(float x) {
-  // tanh(x) = 2*sigmoid(2x) - 1, with the exponent clamped so that __expf never overflows
-  const float e = __expf(-2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
-  return __fdividef(1.0f - e, 1.0f + e);
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 }  // namespace ptx
 
+constexpr int LSTM_NB = 16;                 // batch columns per cluster (tcgen05 M=128 needs N % 16 == 0)
+
 struct LstmFwdParams {
   int T, B, H, n_pre;
-  const float* pre;        // [n_pre, B, 4H]
-  const float* bias;       // [4H]
-  const float* h0;         // [B,H] or null
-  const float* c0;         // [B,H] or null
-  __nv_bfloat16* out;      // [T,B,H]
-  __nv_bfloat16* gates;    // [T,B,4H] or null
-  float* cells;            // [T,B,H] or null
-  float* hT;               // [B,H] or null
-  float* cT;               // [B,H] or null
+  const float* pre;                // [n_pre, B, 4H]
+  const float* bias;               // [4H]
+  const __nv_bfloat16* w;          // [4H, H] bf16 (TMEM-resident path reads it directly)
+  const float* h0;                 // [B,H] or null
+  const float* c0;                 // [B,H] or null
+  __nv_bfloat16* out;              // [T,B,H]
+  __nv_bfloat16* gates;            // kernel-private stash [T][nbt][CS][NB][32][4] or null
+  float* cells;                    // kernel-private stash [T][nbt][CS][NB][32] or null
+  float* hT;                       // [B,H] or null
+  float* cT;                       // [B,H] or null
+  long long* trace;                // debug: [TRACE_STEPS][8] clock64 stamps of CTA 0, or null
+  int dbg_flags;
 };
+constexpr int TRACE_STEPS = 32, TRACE_T0 = 16;
+__device__ long long g_lstm_trace[TRACE_STEPS * 8];
+static bool g_trace_enabled = false;
+static int g_dbg_flags = 0;                 // 8 = keep W in shared memory (the v1 data path) instead of TMEM
+#define S2VT_TRACE(slot)                                                                              \
+  do {                                                                                                \
+    if (p.trace && blockIdx.x == 0 && t >= TRACE_T0 && t < TRACE_T0 + TRACE_STEPS)                    \
+      p.trace[(t - TRACE_T0) * 8 + (slot)] = clock64();                                               \
+  } while (0)
 
-template <int NB>
+template <int NB, bool W_TMEM>
 __global__ void __launch_bounds__(160, 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdParams p) {
-  static_assert(NB % 16 == 0 && NB <= 64, "tcgen05 M=128 needs N % 16 == 0");
-  constexpr int COLS_PER_THREAD = NB / 4;          // phase-2 columns per thread
-  constexpr uint32_t LBO_H = (NB / 8) * 128;       // K-direction stride between 8x16B core matrices of h^T
-  constexpr uint32_t SLICE_BYTES = 4 * LBO_H;      // one CTA's 32 hidden units x NB batch, bf16
+  static_assert(NB == 16, "thread mapping below assumes 16 batch columns per cluster (4 per epilogue warp)");
+  constexpr int CPT = NB / 4;                       // phase-2 columns per thread
+  constexpr uint32_t LBO_H = (NB / 8) * 128;        // K-direction stride between 8x16B core matrices of h^T
+  constexpr uint32_t SLICE_BYTES = 4 * LBO_H;       // one CTA's 32 hidden units x NB batch, bf16
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full, h_full[2], mma_done;
   __shared__ uint32_t tmem_slot;
 
   const int H = p.H, KC = H / 64, CS = H / 32;
-  const uint32_t W_BYTES = 128u * (uint32_t)H * 2u, HBUF_BYTES = (uint32_t)NB * (uint32_t)H * 2u;
+  const uint32_t W_BYTES = W_TMEM ? 0u : 128u * (uint32_t)H * 2u, HBUF_BYTES = (uint32_t)NB * (uint32_t)H * 2u;
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sW = base, sH0 = sW + W_BYTES, sStage0 = sH0 + 2 * HBUF_BYTES, sGu = sStage0 + 2 * SLICE_BYTES;
+  const uint32_t sW = base, sH0 = sW + W_BYTES;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));            // generic pointer to the aligned base
   uint8_t* gH0 = gen + W_BYTES;
-  uint8_t* gStage0 = gH0 + 2 * HBUF_BYTES;
-  float* sG = reinterpret_cast<float*>(gStage0 + 2 * SLICE_BYTES);      // [4 gates][NB][32 units]
-  (void)sGu;
+  float* sG = reinterpret_cast<float*>(gH0 + 2 * HBUF_BYTES);            // [2][4 gates][NB][32 units] fp32
+  __nv_bfloat16* sSt = reinterpret_cast<__nv_bfloat16*>(sG + 2 * 4 * NB * 32);   // [2][NB][32][4] bf16 stash staging
+  uint8_t* sPk = reinterpret_cast<uint8_t*>(sSt + 2 * NB * 32 * 4);      // [4 warps][16 chunks][16 B] h packing
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t c = ptx::cluster_ctarank();                              // hidden-unit slice of this CTA
-  const int b0 = (blockIdx.x / CS) * NB;                                  // batch tile of this cluster
+  const int bt = blockIdx.x / CS, nbt = gridDim.x / CS;
+  const int b0 = bt * NB;                                                 // batch tile of this cluster
   const int T = p.T;
+  const uint32_t tmem_cols = W_TMEM ? (H >= 512 ? 512u : (H >= 256 ? 256u : (H >= 128 ? 128u : 64u))) : 32u;
 
   if (warp == 4 && ptx::elect_one()) {
-    ptx::prefetch_tmap(&tmW);
+    if (!W_TMEM) ptx::prefetch_tmap(&tmW);
     ptx::mbar_init(ptx::smem_u32(&w_full), 1);
     ptx::mbar_init(ptx::smem_u32(&h_full[0]), 1);
     ptx::mbar_init(ptx::smem_u32(&h_full[1]), 1);
@@ -103,10 +143,10 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), 32);
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_slot), tmem_cols);
     ptx::tmem_relinquish();
   }
-  // initial h^T buffer (step 0 input): zeros or h0 in the canonical layout; c state into registers (below)
+  // initial h^T buffer (step 0 input): zeros or h0 in the canonical layout
   if (warp < 4) {
     for (int idx = threadIdx.x; idx < NB * H / 8; idx += 128) {           // one 16-byte chunk (8 k-elements) per iteration
       const int kblk = idx / NB, b = idx % NB;
@@ -125,22 +165,44 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_acc = W_TMEM ? tmem + (uint32_t)(H / 2) : tmem;     // accumulator columns sit after the weight columns
+  if (W_TMEM && warp < 4) {
+    // thread (gate g = warp, unit u = lane) owns TMEM lane 32g+u = gate row g*H + 32c + u of W_hh: two bf16 per 32-bit column
+    const uint4* src = reinterpret_cast<const uint4*>(p.w + ((long long)warp * H + 32 * (int)c + lane) * H);
+    for (int cc = 0; cc < H / 64; ++cc) {
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 v = __ldg(src + cc * 8 + i);
+        r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      }
+      ptx::tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), r);
+    }
+    ptx::tc_wait_st();
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  ptx::tc_fence_after();
   ptx::cluster_arrive();                                                  // every peer's barriers are initialised before
   ptx::cluster_wait();                                                    // anyone signals them remotely
-  const uint32_t tmem = tmem_slot;
 
   if (warp == 4) {
-    // ===================== control thread: weight load, per-step MMA issue =====================
+    // ===================== control thread: (weight load,) per-step MMA issue =====================
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&w_full), W_BYTES);
-      for (int kc = 0; kc < KC; ++kc)
-        for (int g = 0; g < 4; ++g)                                       // rows [g*H + 32c, +32) -> tile rows [32g, 32g+32)
-          ptx::tma_load_2d(sW + kc * 16384 + g * 4096, &tmW, ptx::smem_u32(&w_full), kc * 64, g * H + 32 * (int)c);
-      bool ok = ptx::mbar_wait(ptx::smem_u32(&w_full), 0);
-      if (!ok) atomicExch(&g_sm100_error, 11);
+      bool ok = true;
+      if (!W_TMEM) {
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&w_full), W_BYTES);
+        for (int kc = 0; kc < KC; ++kc)
+          for (int g = 0; g < 4; ++g)                                     // rows [g*H + 32c, +32) -> tile rows [32g, 32g+32)
+            ptx::tma_load_2d(sW + kc * 16384 + g * 4096, &tmW, ptx::smem_u32(&w_full), kc * 64, g * H + 32 * (int)c);
+        ok = ptx::mbar_wait(ptx::smem_u32(&w_full), 0);
+        if (!ok) atomicExch(&g_sm100_error, 11);
+      }
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
       uint32_t ph[2] = {0, 0};
       const bool have_h0 = p.h0 != nullptr;
+      const uint64_t db_base[2] = {ptx::make_smem_desc(sH0, LBO_H, 128, 0), ptx::make_smem_desc(sH0 + HBUF_BYTES, LBO_H, 128, 0)};
       for (int t = 0; t < T && ok; ++t) {
         const int pb = t & 1;
         if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[pb ^ 1]), (uint32_t)CS * SLICE_BYTES);   // h_t lands here
@@ -148,19 +210,27 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
           ok = ptx::mbar_wait(ptx::smem_u32(&h_full[pb]), ph[pb]);
           ph[pb] ^= 1;
           if (!ok) { atomicExch(&g_sm100_error, 12); break; }
+          ptx::fence_proxy_async();                                       // peers' st.async data -> visible to the tensor core
         }
+        S2VT_TRACE(0);
         if (t > 0 || have_h0) {
           ptx::tc_fence_after();
-          const uint32_t sHp = sH0 + pb * HBUF_BYTES;
-          for (int kc = 0; kc < KC; ++kc) {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t da = ptx::make_smem_desc(sW + kc * 16384 + k4 * 32, 16, 1024, 2);
-              const uint64_t db = ptx::make_smem_desc(sHp + (kc * 8 + k4 * 2) * LBO_H, LBO_H, 128, 0);
-              ptx::mma_bf16_ss(tmem, da, db, idesc, (kc | k4) != 0 ? 1u : 0u);
+          // descriptors advance by constants: one 16-wide k-step = 2 core-matrix columns of h^T (2*LBO_H bytes)
+          uint64_t db = db_base[pb];
+          uint32_t ta = tmem;
+#pragma unroll 4
+          for (int ks = 0; ks < 4 * KC; ++ks) {
+            if (W_TMEM) {
+              ptx::mma_bf16_ts(tmem_acc, ta, db, idesc, ks != 0 ? 1u : 0u);
+            } else {
+              const uint64_t da = ptx::make_smem_desc(sW + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2);
+              ptx::mma_bf16_ss(tmem_acc, da, db, idesc, ks != 0 ? 1u : 0u);
             }
+            db += (2 * LBO_H) >> 4;
+            ta += 8;
           }
           ptx::mma_commit(ptx::smem_u32(&mma_done));
+          S2VT_TRACE(1);
         } else {
           ptx::mbar_arrive(ptx::smem_u32(&mma_done));                     // h_{-1} = 0: nothing to multiply
         }
@@ -171,43 +241,70 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
     const int g = warp;                       // phase 1: gate row block of this warp (i,f,g,o) == TMEM lane quarter
     const int u = lane;                       // hidden unit within the CTA slice
     const int unit = 32 * (int)c + u;
-    const int q = warp;                       // phase 2: column group
-    float creg[COLS_PER_THREAD];
+    const int q = warp;                       // phase 2: column group (columns 4q .. 4q+3)
+    float creg[CPT];
 #pragma unroll
-    for (int j = 0; j < COLS_PER_THREAD; ++j) {
-      const int b = b0 + q * COLS_PER_THREAD + j;
+    for (int j = 0; j < CPT; ++j) {
+      const int b = b0 + q * CPT + j;
       creg[j] = (p.c0 && b < p.B) ? p.c0[(long long)b * H + unit] : 0.f;
     }
     const float bias_g = p.bias[g * H + unit];
+    const float sc = (g == 2) ? 1.0f : 0.5f, sh = (g == 2) ? 0.0f : 0.5f;     // tanh for the g gate, sigmoid otherwise
     float pre_cur[NB];
+    // columns past the batch are clamped to the last row (finite garbage that is never stored) so that the loads stay
+    // unconditional: a select on the loaded value would stall this warp for a full memory latency
+    const float* pre_row0 = p.pre + (long long)min(b0, p.B - 1) * 4 * H + g * H + unit;
+    const int row_stride = (b0 + NB <= p.B) ? 4 * H : 0;               // ragged last tile: every column reads one valid row...
+    const long long step_stride = (long long)p.B * 4 * H;
     auto load_pre = [&](int t, float (&dst)[NB]) {
       if (t < p.n_pre) {
-        const float* src = p.pre + ((long long)t * p.B + b0) * 4 * H + g * H + unit;
+        const float* src = pre_row0 + t * step_stride;
+        if (row_stride != 0) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) dst[j] = (b0 + j < p.B) ? __ldg(src + (long long)j * 4 * H) : 0.f;
+          for (int j = 0; j < NB; ++j) dst[j] = __ldg(src + j * row_stride);
+        } else {                                                        // ...unless it exists (slow path, partial tile only)
+#pragma unroll
+          for (int j = 0; j < NB; ++j) dst[j] = __ldg(src + (long long)(min(b0 + j, p.B - 1) - min(b0, p.B - 1)) * 4 * H);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < NB; ++j) dst[j] = bias_g;
       }
     };
     load_pre(0, pre_cur);
+    // st.async targets: this lane serves h chunk (m = octet of units, colL = column within the warp's four) to 8 peers
+    const int chunk = lane & 15, colL = chunk >> 2, m = chunk & 3;
+    const int bcol = q * CPT + colL;
+    const uint32_t chunk_off = c * SLICE_BYTES + (uint32_t)((m * (NB / 8) + bcol / 8) * 128 + (bcol % 8) * 16);
+    const int peer0 = (lane >> 4) * 8;
+    uint32_t peer_h[8], peer_bar[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t peer = (uint32_t)min(peer0 + i, CS - 1);
+      peer_h[i] = ptx::mapa(sH0, peer) + chunk_off;
+      peer_bar[i] = ptx::mapa(ptx::smem_u32(&h_full[0]), peer);
+    }
+    const uint32_t bar_stride = ptx::smem_u32(&h_full[1]) - ptx::smem_u32(&h_full[0]);
+    uint8_t* myPk = sPk + warp * 256;
+    const long long stash_blk = ((long long)nbt * CS);                    // blocks per timestep
     const bool have_h0 = p.h0 != nullptr;
     bool ok = true;
     for (int t = 0; t < T; ++t) {
+      const int sb = t & 1;
+      float* sGb = sG + sb * (4 * NB * 32);
+      __nv_bfloat16* sStb = sSt + sb * (NB * 32 * 4);
       // ---- phase 1: accumulator + pre-activation -> activation -> smem
       ok = ok && ptx::mbar_wait(ptx::smem_u32(&mma_done), (uint32_t)(t & 1));
       if (!ok) { atomicExch(&g_sm100_error, 13); break; }
+      if (threadIdx.x == 0) S2VT_TRACE(2);
       float x[NB];
       if (t > 0 || have_h0) {
         ptx::tc_fence_after();
         uint32_t r[16];
+        ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
+        ptx::tc_wait_ld();
 #pragma unroll
-        for (int cc = 0; cc < NB / 16; ++cc) {
-          ptx::tmem_ld_32x16(tmem + ((uint32_t)(warp * 32) << 16) + cc * 16, r);
-          ptx::tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[cc * 16 + j] = __uint_as_float(r[j]) + pre_cur[cc * 16 + j];
-        }
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(r[j]) + pre_cur[j];
         ptx::tc_fence_before();
       } else {
 #pragma unroll
@@ -216,49 +313,62 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       if (t + 1 < T) load_pre(t + 1, pre_cur);                            // prefetch: latency hides behind the rest of the step
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const float a = (g == 2) ? ptx::fast_tanh(x[j]) : ptx::fast_sigmoid(x[j]);
-        sG[(g * NB + j) * 32 + u] = a;
-        x[j] = a;
+        const float a = fmaf(sc, ptx::fast_tanh(sc * x[j]), sh);
+        sGb[(g * NB + j) * 32 + u] = a;
+        sStb[(j * 32 + u) * 4 + g] = __float2bfloat16(a);
       }
-      if (p.gates) {
-        __nv_bfloat16* gdst = p.gates + ((long long)t * p.B + b0) * 4 * H + g * H + unit;
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-          if (b0 + j < p.B) gdst[(long long)j * 4 * H] = __float2bfloat16(x[j]);
-      }
+      if (threadIdx.x == 0) S2VT_TRACE(3);
       ptx::named_bar_sync(1, 128);
-      // ---- phase 2: cell / hidden update for (unit u, columns q*CPT .. +CPT)
-      uint8_t* stage = gStage0 + (t & 1) * SLICE_BYTES;
+      if (threadIdx.x == 0) S2VT_TRACE(4);
+      // ---- phase 2: cell / hidden update for (unit u, columns 4q .. 4q+3)
+      float hval[CPT];
 #pragma unroll
-      for (int j = 0; j < COLS_PER_THREAD; ++j) {
-        const int col = q * COLS_PER_THREAD + j;
-        const float gi = sG[(0 * NB + col) * 32 + u], gf = sG[(1 * NB + col) * 32 + u];
-        const float gg = sG[(2 * NB + col) * 32 + u], go = sG[(3 * NB + col) * 32 + u];
+      for (int j = 0; j < CPT; ++j) {
+        const int col = q * CPT + j;
+        const float gi = sGb[(0 * NB + col) * 32 + u], gf = sGb[(1 * NB + col) * 32 + u];
+        const float gg = sGb[(2 * NB + col) * 32 + u], go = sGb[(3 * NB + col) * 32 + u];
         const float cn = gf * creg[j] + gi * gg;
         creg[j] = cn;
-        const float h = go * ptx::fast_tanh(cn);
-        const __nv_bfloat16 hb = __float2bfloat16(h);
-        *reinterpret_cast<__nv_bfloat16*>(stage + ((u / 8) * (NB / 8) + col / 8) * 128 + (col % 8) * 16 + (u % 8) * 2) = hb;
-        const int b = b0 + col;
-        if (b < p.B) {
-          const long long o = ((long long)t * p.B + b) * H + unit;
-          p.out[o] = hb;
-          if (p.cells) p.cells[o] = cn;
-          if (t == T - 1) {
-            if (p.hT) p.hT[(long long)b * H + unit] = h;
-            if (p.cT) p.cT[(long long)b * H + unit] = cn;
+        hval[j] = go * ptx::fast_tanh(cn);
+        *reinterpret_cast<__nv_bfloat16*>(myPk + ((j * 4 + (u >> 3)) * 8 + (u & 7)) * 2) = __float2bfloat16(hval[j]);
+      }
+      __syncwarp();
+      const uint4 hchunk = *reinterpret_cast<const uint4*>(myPk + chunk * 16);    // 8 units x 1 column, bf16
+      if (threadIdx.x == 0) S2VT_TRACE(5);
+      // ---- h_t to every peer's next-step buffer (critical path first)
+      if (t + 1 < T) {
+        const uint32_t boff = (uint32_t)((t + 1) & 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (peer0 + i < CS) ptx::st_async_16(peer_h[i] + boff * HBUF_BYTES, hchunk, peer_bar[i] + boff * bar_stride);
+      }
+      if (threadIdx.x == 0) S2VT_TRACE(6);
+      // ---- off the critical path: h_t, c_t and the gate activations to HBM
+      if (lane < 16 && b0 + bcol < p.B)
+        *reinterpret_cast<uint4*>(p.out + ((long long)t * p.B + b0 + bcol) * H + 32 * (int)c + 8 * m) = hchunk;
+      const long long blk = (long long)t * stash_blk + (long long)bt * CS + c;
+      if (p.cells) {
+        float* cdst = p.cells + blk * (NB * 32) + u;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) cdst[(q * CPT + j) * 32] = creg[j];
+      }
+      if (p.gates) {
+        const uint4* ssrc = reinterpret_cast<const uint4*>(sStb);
+        uint4* gdst = reinterpret_cast<uint4*>(p.gates + blk * (NB * 32 * 4));
+        gdst[threadIdx.x] = ssrc[threadIdx.x];
+        gdst[threadIdx.x + 128] = ssrc[threadIdx.x + 128];
+      }
+      if (t == T - 1) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int b = b0 + q * CPT + j;
+          if (b < p.B) {
+            if (p.hT) p.hT[(long long)b * H + unit] = hval[j];
+            if (p.cT) p.cT[(long long)b * H + unit] = creg[j];
           }
         }
       }
-      if (t + 1 < T) {
-        ptx::fence_proxy_async();                                         // staging writes -> visible to the bulk-copy engine
-        ptx::named_bar_sync(1, 128);
-        if (warp == 0 && lane < CS) {
-          const uint32_t dst = ptx::mapa(sH0 + ((t + 1) & 1) * HBUF_BYTES + c * SLICE_BYTES, (uint32_t)lane);
-          const uint32_t bar = ptx::mapa(ptx::smem_u32(&h_full[(t + 1) & 1]), (uint32_t)lane);
-          ptx::bulk_copy_to_peer(dst, sStage0 + (t & 1) * SLICE_BYTES, SLICE_BYTES, bar);
-        }
-      }
+      if (threadIdx.x == 0) S2VT_TRACE(7);
     }
   }
   // no CTA may exit while peers can still write into its shared memory
@@ -266,14 +376,15 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
   __syncthreads();
   ptx::cluster_arrive();
   ptx::cluster_wait();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 32);
+  if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
 }
 
-template <int NB>
+template <int NB, bool W_TMEM>
 static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFwdParams& p) {
   const int H = p.H, CS = H / 32;
-  const size_t smem = 1024 + (size_t)128 * H * 2 + 2 * (size_t)NB * H * 2 + 2 * (size_t)(4 * (NB / 8) * 128) + (size_t)4 * NB * 32 * 4;
-  auto kern = lstm_fwd_cluster_kernel<NB>;
+  const size_t smem = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + 2 * (size_t)NB * H * 2 + 2 * (size_t)4 * NB * 32 * 4 +
+                      2 * (size_t)NB * 32 * 4 * 2 + 4 * 256;
+  auto kern = lstm_fwd_cluster_kernel<NB, W_TMEM>;
   S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (CS > 8) S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
@@ -297,6 +408,8 @@ static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFw
 
 using namespace s2vt;
 
+extern "C" int64_t s2vt_lstm_bf16_batch_pad(int B) { return (int64_t)ceil_div(B, LSTM_NB) * LSTM_NB; }
+
 extern "C" int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
                                   const float* pre, const float* bias_sum, const void* w_hh_bf16,
                                   const float* h0, const float* c0,
@@ -306,12 +419,34 @@ extern "C" int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
   S2VT_REQUIRE(bias_sum && w_hh_bf16 && out_bf16, "s2vt_lstm_fwd_bf16: null pointer");
   S2VT_REQUIRE(n_pre <= 0 || pre, "s2vt_lstm_fwd_bf16: pre is null but n_pre > 0");
   S2VT_REQUIRE((h0 == nullptr) == (c0 == nullptr), "s2vt_lstm_fwd_bf16: h0 and c0 must be given together");
-  CUtensorMap tmW;
-  int rc = make_tmap_bf16(&tmW, w_hh_bf16, (uint64_t)H, (uint64_t)4 * H, (uint64_t)H, 64, 32);
-  if (rc) return rc;
+  S2VT_REQUIRE(aligned16(w_hh_bf16) && aligned16(out_bf16) && (!gates_bf16 || aligned16(gates_bf16)), "s2vt_lstm_fwd_bf16: buffers must be 16-byte aligned");
   LstmFwdParams p{};
   p.T = T; p.B = B; p.H = H; p.n_pre = n_pre < 0 ? 0 : n_pre;
-  p.pre = pre; p.bias = bias_sum; p.h0 = h0; p.c0 = c0;
+  p.pre = pre; p.bias = bias_sum; p.w = (const __nv_bfloat16*)w_hh_bf16; p.h0 = h0; p.c0 = c0;
   p.out = (__nv_bfloat16*)out_bf16; p.gates = (__nv_bfloat16*)gates_bf16; p.cells = cells; p.hT = hT; p.cT = cT;
-  return launch_lstm_fwd<16>((cudaStream_t)stream, tmW, p);
+  p.trace = nullptr;
+  p.dbg_flags = g_dbg_flags;
+  if (g_trace_enabled) {
+    void* sym = nullptr;
+    S2VT_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_lstm_trace));
+    p.trace = (long long*)sym;
+  }
+  CUtensorMap tmW;
+  if (g_dbg_flags & 8) {
+    int rc = make_tmap_bf16(&tmW, w_hh_bf16, (uint64_t)H, (uint64_t)4 * H, (uint64_t)H, 64, 32);
+    if (rc) return rc;
+    return launch_lstm_fwd<LSTM_NB, false>((cudaStream_t)stream, tmW, p);
+  }
+  memset(&tmW, 0, sizeof(tmW));
+  return launch_lstm_fwd<LSTM_NB, true>((cudaStream_t)stream, tmW, p);
+}
+
+// debug aids (not part of the product path): per-step clock64 stamps of CTA 0 for steps [16, 48)
+extern "C" int s2vt_debug_trace_enable(int on) { g_trace_enabled = on != 0; return 0; }
+extern "C" int s2vt_debug_set_flags(int flags) { g_dbg_flags = flags; return 0; }
+extern "C" int s2vt_debug_trace_read(long long* host_out, int n) {
+  if (n > TRACE_STEPS * 8) n = TRACE_STEPS * 8;
+  S2VT_CHECK_CUDA(cudaDeviceSynchronize());
+  S2VT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_lstm_trace, sizeof(long long) * n));
+  return 0;
 }

@@ -47,16 +47,21 @@ def run_lstm_bf16(dev, T, B, H, n_pre, with_state=False, seed=0):
     pre = (torch.randn(max(n_pre, 1), B, 4 * H, generator=g) * 0.7).to(dev)
     h0 = (torch.randn(B, H, generator=g) * 0.3).to(dev) if with_state else None
     c0 = (torch.randn(B, H, generator=g) * 0.5).to(dev) if with_state else None
-    out = torch.full((T, B, H), float("nan"), device=dev, dtype=torch.bfloat16)
-    gates = torch.full((T, B, 4 * H), float("nan"), device=dev, dtype=torch.bfloat16)
-    cells = torch.full((T, B, H), float("nan"), device=dev)
-    hT = torch.empty(B, H, device=dev); cT = torch.empty(B, H, device=dev)
     lib = L.load()
+    Bp = int(lib.s2vt_lstm_bf16_batch_pad(B))
+    out = torch.full((T, B, H), float("nan"), device=dev, dtype=torch.bfloat16)
+    gates = torch.full((T * Bp * 4 * H,), float("nan"), device=dev, dtype=torch.bfloat16)
+    cells = torch.full((T * Bp * H,), float("nan"), device=dev)
+    hT = torch.empty(B, H, device=dev); cT = torch.empty(B, H, device=dev)
     rc = lib.s2vt_lstm_fwd_bf16(L.stream_ptr(dev), T, B, H, n_pre, L.ptr(pre), L.ptr(bias), L.ptr(wb), L.ptr(h0), L.ptr(c0),
                                 L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT))
     L.check(rc, "s2vt_lstm_fwd_bf16")
     flag = lib.s2vt_device_error_flag(L.stream_ptr(dev))
     assert flag == 0, "device error flag %d" % flag
+    # undo the kernel-private stash layout: gates [T][nbt][CS][16][32][4], cells [T][nbt][CS][16][32]
+    nbt, CS = Bp // 16, H // 32
+    gates = gates.view(T, nbt, CS, 16, 32, 4).permute(0, 1, 3, 5, 2, 4).reshape(T, Bp, 4 * H)[:, :B]
+    cells = cells.view(T, nbt, CS, 16, 32).permute(0, 1, 3, 2, 4).reshape(T, Bp, H)[:, :B]
     ro, rg, rc_, rh, rcT = lstm_ref(pre, bias, wb.float(), T, n_pre, h0, c0)
     return (out, gates, cells, hT, cT), (ro, rg, rc_, rh, rcT)
 
@@ -91,6 +96,7 @@ def test_lstm_fwd_bf16_speed(dev):
     gates = torch.empty(T, B, 4 * H, device=dev, dtype=torch.bfloat16)
     cells = torch.empty(T, B, H, device=dev)
     lib = L.load()
+    assert int(lib.s2vt_lstm_bf16_batch_pad(B)) == B
 
     def run():
         rc = lib.s2vt_lstm_fwd_bf16(L.stream_ptr(dev), T, B, H, T, L.ptr(pre), L.ptr(bias), L.ptr(wb), None, None,
