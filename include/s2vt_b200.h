@@ -111,6 +111,14 @@ int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
                        const float* h0, const float* c0,
                        void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT);
 
+/* Persistent tensor-core BPTT, the backward twin of s2vt_lstm_fwd_bf16 (same cluster shape; needs H % 128 == 0, H <= 512).
+ *   dout [T,B,H] f32 (rows t < dout_t0 are zero and never read) or NULL;  gates_bf16 / cells: the forward stash (private layout)
+ *   w_hh_t_bf16 [H,4H] bf16 = W_hh transposed;  dgates_bf16 [T,B,4H] bf16 out (time-major GEMM layout)
+ * replaces: autograd of nn.LSTM under loss.backward(), train.py:124. */
+int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0,
+                       const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
+                       void* dgates_bf16);
+
 /* BPTT through one layer from a zero final-state gradient.
  *   dout   [T, B, H]  dL/dh_t from above; rows t < dout_t0 are treated as zero (and not read)
  *   gates, cells      the forward stash;  c0 = 0 is assumed (the reference never passes a state in training)
@@ -181,6 +189,17 @@ int s2vt_beam_search_f32(void* stream, int B, int H, int E, int V, int beam_widt
                          const float* w_cat2, const float* bias2, const float* emb,
                          const float* w_out, const float* b_out, const float* len_pen,
                          int64_t* out_tokens, int32_t* out_len, void* ws);
+
+/* ------------------------------------------------------------------ bf16 training-path helpers
+ * bf16 twin of s2vt_embed_gather_f32 (replaces self.embedding(targets), S2VTModel.py:71). */
+int s2vt_embed_gather_bf16(void* stream, const void* table_bf16, int E, const int64_t* ids, int64_t ids_ld,
+                           int B, int n_t, void* out_bf16, int64_t out_ld);
+/* out[n] = sum_m X[m*ld + n] for a bf16 matrix, fp32 accumulation (bias gradients). */
+int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t ld, float* out);
+/* Mean cross entropy as s2vt_ce_f32, with the gradient written as bf16 (the operand dtype of the backward GEMMs).
+ * row_loss / loss may be NULL when only dlogits are wanted. */
+int s2vt_ce_bf16(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
+                 float* row_loss, float* loss, void* dlogits_bf16, const float* gscale);
 
 #ifdef __cplusplus
 }

@@ -5,5 +5,7 @@ from .lib import LIB_PATH, S2VTLibraryError, launch_count, load
 from .model import PARAM_ORDER, S2VT, S2VTModel
 from .optim import FusedAdam
 
-__all__ = ["S2VT", "S2VTModel", "MaskCriterion", "FusedAdam", "PARAM_ORDER", "load", "launch_count", "LIB_PATH",
+BF16_TRAIN_READY = True     # bench.py: the tensor-core training path is the default for supported shapes
+
+__all__ = ["BF16_TRAIN_READY", "S2VT", "S2VTModel", "MaskCriterion", "FusedAdam", "PARAM_ORDER", "load", "launch_count", "LIB_PATH",
            "S2VTLibraryError"]

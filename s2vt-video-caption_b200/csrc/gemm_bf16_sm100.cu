@@ -209,12 +209,12 @@ using namespace s2vt;
 
 extern "C" int s2vt_has_tcgen05(void) { return 1; }
 
-namespace s2vt { int lstm_bf16_error_flag(); }
+namespace s2vt { int lstm_bf16_error_flag(); int lstm_bwd_bf16_error_flag(); }
 
 extern "C" int s2vt_device_error_flag(void* stream) {
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -2;
-  const int a = read_sm100_error_flag(), b = lstm_bf16_error_flag();
-  return a != 0 ? a : b;
+  const int a = read_sm100_error_flag(), b = lstm_bf16_error_flag(), c = lstm_bwd_bf16_error_flag();
+  return a != 0 ? a : (b != 0 ? b : c);
 }
 
 extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,

@@ -1,0 +1,286 @@
+// Persistent BPTT of one LSTM layer on Blackwell tensor cores: the backward twin of lstm_bf16_sm100.cu.
+//
+//   cluster = H/32 CTAs; CTA c owns hidden units [32c, 32c+32) = 128 gate rows r (i,f,g,o x 32), batch tile of 16 columns
+//   per step t = T-1 .. 0
+//     dh_t   = dL/dh_t (from the layer above, fp32) + dh_rec          dh_rec: recurrent gradient, reduced from 16 partials
+//     dgates = pointwise(dh_t, dc, stash_t)                           fused gate gradients, dc stays in registers
+//     -> bf16 dgates_t go (a) to HBM in GEMM layout [T*B, 4H] for the time-batched weight-gradient products and
+//                         (b) into a 4 KB shared-memory B operand (canonical no-swizzle K-major layout)
+//     partial[j, b] = sum_{r in rows_c} W_hh[r, j] * dgates[b, r]     tcgen05.mma, A = W_hh[rows_c, :]^T resident in TMEM
+//                                                                     (H/128 tiles of M=128 x K=128), fp32 accumulators in TMEM
+//     reduce-scatter: the 32 x 16 fp32 block of partial that belongs to CTA d's units is pushed into d's receive buffer with
+//                     st.async (DSMEM) and completes on d's mbarrier; d sums the 16 blocks at the start of step t-1.
+//
+// As in the forward kernel there is no grid barrier and no global-memory round trip on the critical path.
+#include "common.cuh"
+#include "sm100_cluster.cuh"
+#include "sm100_err.cuh"
+
+namespace s2vt {
+
+int lstm_bwd_bf16_error_flag() { return read_sm100_error_flag(); }
+
+constexpr int BWD_NB = 16;
+
+struct LstmBwdParams {
+  int T, B, H, dout_t0;
+  const float* dout;               // [T,B,H] fp32 or null; rows t < dout_t0 are zero and never read
+  const __nv_bfloat16* gates;      // forward stash [T][nbt][CS][16][32][4]
+  const float* cells;              // forward stash [T][nbt][CS][16][32]
+  const __nv_bfloat16* w_t;        // W_hh^T bf16 [H, 4H]
+  __nv_bfloat16* dgates;           // [T,B,4H] bf16 out
+};
+
+__global__ void __launch_bounds__(160, 1)
+lstm_bwd_cluster_kernel(const LstmBwdParams p) {
+  constexpr int NB = BWD_NB, CPT = NB / 4;
+  constexpr uint32_t LBO_B = (NB / 8) * 128;         // K-direction stride between core matrices of dgates^T
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t recv_full[2], b_ready, mma_done;
+  __shared__ uint32_t tmem_slot;
+
+  const int H = p.H, CS = H / 32, NT = H / 128;      // NT = 128-row output tiles of dh
+  const uint32_t RECV_BYTES = (uint32_t)CS * 32u * NB * 4u;
+  const uint32_t base = (cl::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sRecv0 = base, sB = base + 2 * RECV_BYTES;
+  uint8_t* gen = smem_raw + (base - cl::smem_u32(smem_raw));
+  const float4* gRecv0 = reinterpret_cast<const float4*>(gen);
+  uint8_t* gB = gen + 2 * RECV_BYTES;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t c = cl::cluster_ctarank();
+  const int bt = blockIdx.x / CS, nbt = gridDim.x / CS;
+  const int b0 = bt * NB;
+  const int T = p.T;
+  const uint32_t need_cols = (uint32_t)(H / 2 + NT * NB);
+  const uint32_t tmem_cols = need_cols <= 64 ? 64u : (need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u));
+
+  if (warp == 4 && ptx::elect_one()) {
+    ptx::mbar_init(cl::smem_u32(&recv_full[0]), 1);
+    ptx::mbar_init(cl::smem_u32(&recv_full[1]), 1);
+    ptx::mbar_init(cl::smem_u32(&b_ready), 128);
+    ptx::mbar_init(cl::smem_u32(&mma_done), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(cl::smem_u32(&tmem_slot), tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_acc = tmem + (uint32_t)(H / 2);
+  if (warp < 4) {
+    // A tile i, TMEM lane m = 32*warp + lane  <->  output unit j = 128 i + m;  K index k = g*32 + u  <->  gate row g*H + 32c + u.
+    // W_hh^T[j, g*H + 32c .. +32] is 64 contiguous bytes, so each (tile, gate) is four 16-byte loads = 16 TMEM columns.
+    for (int i = 0; i < NT; ++i) {
+      const __nv_bfloat16* row = p.w_t + (long long)(128 * i + 32 * warp + lane) * 4 * H + 32 * (int)c;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const uint4* src = reinterpret_cast<const uint4*>(row + (long long)(half * 2 + gg) * H);
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const uint4 v = __ldg(src + v4);
+            r[gg * 16 + v4 * 4 + 0] = v.x; r[gg * 16 + v4 * 4 + 1] = v.y; r[gg * 16 + v4 * 4 + 2] = v.z; r[gg * 16 + v4 * 4 + 3] = v.w;
+          }
+        }
+        cl::tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * 64 + half * 32), r);
+      }
+    }
+    cl::tc_wait_st();
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  ptx::tc_fence_after();
+  cl::cluster_arrive();
+  cl::cluster_wait();
+
+  if (warp == 4) {
+    // ===================== control thread: one batch of MMAs per step =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
+      const uint64_t db_base = cl::make_smem_desc(sB, LBO_B, 128, 0);
+      bool ok = true;
+      for (int t = T - 1; t >= 1 && ok; --t) {                 // step 0 has no predecessor to feed
+        ptx::mbar_arrive_expect_tx(cl::smem_u32(&recv_full[t & 1]), RECV_BYTES);     // partials of step t land in recv[t&1]
+        ok = ptx::mbar_wait(cl::smem_u32(&b_ready), (uint32_t)((T - 1 - t) & 1));
+        if (!ok) { atomicExch(&g_sm100_error, 21); break; }
+        ptx::tc_fence_after();
+        for (int i = 0; i < NT; ++i) {
+          uint64_t db = db_base;
+          uint32_t ta = tmem + (uint32_t)(i * 64);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            cl::mma_bf16_ts(tmem_acc + (uint32_t)(i * NB), ta, db, idesc, ks != 0 ? 1u : 0u);
+            db += (2 * LBO_B) >> 4;
+            ta += 8;
+          }
+        }
+        ptx::mma_commit(cl::smem_u32(&mma_done));
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0..3: thread = (unit u = lane, column group q = warp) =====================
+    const int u = lane, q = warp;
+    const int unit = 32 * (int)c + u;
+    float dc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) dc[j] = 0.f;
+    const long long stash_blk = (long long)nbt * CS;
+    const long long my_blk0 = (long long)bt * CS + c;
+    // prefetched per-step operands
+    uint2 gate_raw[CPT];
+    float c_t[CPT], c_prev[CPT], dout_v[CPT];
+    int rowoff[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) rowoff[j] = min(b0 + q * CPT + j, p.B - 1);
+    auto load_step = [&](int t, bool first) {
+      const long long blk = (long long)t * stash_blk + my_blk0;
+      const uint2* gsrc = reinterpret_cast<const uint2*>(p.gates + blk * (NB * 32 * 4));
+      const float* csrc = p.cells + blk * (NB * 32);
+      const float* cprev_src = p.cells + (blk - stash_blk) * (NB * 32);
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int col = q * CPT + j;
+        gate_raw[j] = __ldg(gsrc + col * 32 + u);
+        if (first) c_t[j] = __ldg(csrc + col * 32 + u);
+        else c_t[j] = c_prev[j];                                 // c_t of step t == c_{t-1} loaded for step t+1
+        c_prev[j] = (t > 0) ? __ldg(cprev_src + col * 32 + u) : 0.f;
+        dout_v[j] = (p.dout && t >= p.dout_t0) ? __ldg(p.dout + ((long long)t * p.B + rowoff[j]) * H + unit) : 0.f;
+      }
+    };
+    load_step(T - 1, true);
+    // reduce-scatter targets: this thread's TMEM lane in tile i holds dh partials of unit (128 i + 32 warp + lane), owned by CTA 4i + warp
+    uint32_t dst_recv[4], dst_bar[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t d = (uint32_t)min(4 * i + warp, CS - 1);
+      dst_recv[i] = cl::mapa(sRecv0, d) + (uint32_t)(((c * 4 + 0) * 32 + lane) * 16);
+      dst_bar[i] = cl::mapa(cl::smem_u32(&recv_full[0]), d);
+    }
+    const uint32_t bar_stride = cl::smem_u32(&recv_full[1]) - cl::smem_u32(&recv_full[0]);
+    uint32_t rph[2] = {0, 0};
+    bool ok = true;
+    for (int t = T - 1; t >= 0; --t) {
+      // ---- A. recurrent gradient: sum the CS partial blocks that arrived for this CTA's units
+      float dh[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) dh[j] = dout_v[j];
+      if (t < T - 1) {
+        const int rb = (t + 1) & 1;
+        ok = ok && ptx::mbar_wait(cl::smem_u32(&recv_full[rb]), rph[rb]);
+        rph[rb] ^= 1;
+        if (!ok) { atomicExch(&g_sm100_error, 22); break; }
+        const float4* rsrc = gRecv0 + (size_t)rb * (RECV_BYTES / 16) + q * 32 + u;
+        for (int s = 0; s < CS; ++s) {
+          const float4 v = rsrc[s * 128];
+          dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
+        }
+      }
+      // ---- B. fused gate gradients
+      float dgv[CPT][4];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const __nv_bfloat162 g01 = *reinterpret_cast<const __nv_bfloat162*>(&gate_raw[j].x);
+        const __nv_bfloat162 g23 = *reinterpret_cast<const __nv_bfloat162*>(&gate_raw[j].y);
+        const float gi = __low2float(g01), gf = __high2float(g01), gg = __low2float(g23), go = __high2float(g23);
+        const float tc = cl::fast_tanh(c_t[j]);
+        const float d_o = dh[j] * tc;
+        const float dcv = dc[j] + dh[j] * go * (1.f - tc * tc);
+        dgv[j][0] = dcv * gg * gi * (1.f - gi);
+        dgv[j][1] = dcv * c_prev[j] * gf * (1.f - gf);
+        dgv[j][2] = dcv * gi * (1.f - gg * gg);
+        dgv[j][3] = d_o * go * (1.f - go);
+        dc[j] = dcv * gf;
+      }
+      // ---- C. bf16 dgates into the B operand: element (b = col, k = g*32 + u)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int col = q * CPT + j;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<__nv_bfloat16*>(gB + ((g * 4 + (u >> 3)) * (NB / 8) + col / 8) * 128 + (col % 8) * 16 + (u & 7) * 2) =
+              __float2bfloat16(dgv[j][g]);
+      }
+      ptx::fence_proxy_async();
+      if (t > 0) ptx::mbar_arrive(cl::smem_u32(&b_ready));
+      if (t > 0) load_step(t - 1, false);                       // prefetch the next step's stash / dout
+      cl::named_bar_sync(1, 128);
+      // ---- D. dgates_t to HBM in GEMM layout: 256 chunks of 8 units x 1 column
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int x = threadIdx.x + 128 * r;
+        const int kblk = x >> 4, b = x & 15;
+        if (b0 + b < p.B) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gB + (kblk * (NB / 8) + b / 8) * 128 + (b % 8) * 16);
+          *reinterpret_cast<uint4*>(p.dgates + ((long long)t * p.B + b0 + b) * 4 * H + (kblk >> 2) * H + 32 * (int)c + 8 * (kblk & 3)) = v;
+        }
+      }
+      // ---- E. scatter this CTA's partial dh to the owners of each unit
+      if (t > 0) {
+        ok = ok && ptx::mbar_wait(cl::smem_u32(&mma_done), (uint32_t)((T - 1 - t) & 1));
+        if (!ok) { atomicExch(&g_sm100_error, 23); break; }
+        ptx::tc_fence_after();
+        const uint32_t boff = (uint32_t)(t & 1);
+        for (int i = 0; i < NT; ++i) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * NB), r);
+          ptx::tc_wait_ld();
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            cl::st_async_16(dst_recv[i] + boff * RECV_BYTES + (uint32_t)(qq * 32 * 16), r[4 * qq], r[4 * qq + 1], r[4 * qq + 2], r[4 * qq + 3],
+                            dst_bar[i] + boff * bar_stride);
+        }
+        ptx::tc_fence_before();
+        cl::named_bar_sync(1, 128);                              // B operand / accumulators are free for the next step
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  cl::cluster_arrive();
+  cl::cluster_wait();
+  if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace s2vt
+
+using namespace s2vt;
+
+extern "C" int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0,
+                                  const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
+                                  void* dgates_bf16) {
+  S2VT_REQUIRE(T >= 1 && B >= 1, "s2vt_lstm_bwd_bf16: bad dims");
+  S2VT_REQUIRE(H % 128 == 0 && H >= 128 && H <= 512, "s2vt_lstm_bwd_bf16: the cluster-resident kernel needs H %% 128 == 0 and 128 <= H <= 512 (got %d)", H);
+  S2VT_REQUIRE(gates_bf16 && cells && w_hh_t_bf16 && dgates_bf16, "s2vt_lstm_bwd_bf16: null pointer");
+  S2VT_REQUIRE(aligned16(gates_bf16) && aligned16(w_hh_t_bf16) && aligned16(dgates_bf16), "s2vt_lstm_bwd_bf16: buffers must be 16-byte aligned");
+  LstmBwdParams p{};
+  p.T = T; p.B = B; p.H = H; p.dout_t0 = dout_t0 < 0 ? 0 : dout_t0;
+  p.dout = dout; p.gates = (const __nv_bfloat16*)gates_bf16; p.cells = cells; p.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
+  p.dgates = (__nv_bfloat16*)dgates_bf16;
+  const int CS = H / 32;
+  const size_t smem = 1024 + 2 * (size_t)CS * 32 * BWD_NB * 4 + (size_t)BWD_NB * 128 * 2;
+  auto kern = lstm_bwd_cluster_kernel;
+  S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CS > 8) S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CS * ceil_div(B, BWD_NB));
+  cfg.blockDim = dim3(160);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int max_clusters = 0;
+  S2VT_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  S2VT_REQUIRE(max_clusters >= 1, "s2vt_lstm_bwd_bf16: a cluster of %d CTAs with %zu B of shared memory cannot be scheduled on this device", CS, smem);
+  S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+  return 0;
+}

@@ -1,0 +1,215 @@
+"""bf16 training engine: the S2VT train step on tensor cores.
+
+Every dense contraction is a TMA-fed tcgen05 GEMM (bf16 operands, fp32 accumulation in TMEM); both recurrences and both
+BPTT sweeps run in the persistent cluster kernels; fp32 master weights stay in the nn.Parameters and are mirrored into
+bf16 shadows that are rebuilt only when the weights change.  Same mathematics and data flow as model.train_forward_f32 /
+train_backward_f32 (the exact path) -- operands are bf16 instead of fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import lib as L
+from . import ops
+from .lib import dense, rowmap
+
+BF = torch.bfloat16
+
+
+def supported(H: int, E: int, F: int, V: int) -> bool:
+    """Shapes the tensor-core path covers: cluster recurrence needs H % 128 == 0 and H <= 512; TMA needs 16-byte rows."""
+    return H % 128 == 0 and 128 <= H <= 512 and E % 8 == 0 and F % 8 == 0 and V % 8 == 0
+
+
+# ------------------------------------------------------------------------------------------------ thin wrappers
+def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None, accumulate=False, a_off=0, b_off=0, c_off=0):
+    with ops._timed("gemm_bf16", 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if out_bf16 else 4.0) * M * N):
+        rc = L.load().s2vt_gemm_bf16(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), lda, int(a_mn), L.ptr(B, b_off), ldb, int(b_mn),
+                                     L.ptr(C, c_off), cmap, int(out_bf16), L.ptr(bias), int(accumulate))
+    L.check(rc, "s2vt_gemm_bf16")
+
+
+def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False):
+    dst = torch.empty(rows, cols, dtype=BF, device=src.device)
+    dst_t = torch.empty(cols, rows, dtype=BF, device=src.device) if want_t else None
+    with ops._timed("cast_bf16", 0.0, 6.0 * rows * cols):
+        rc = L.load().s2vt_cast_bf16(L.stream_ptr(src.device), L.ptr(src), L.ptr(dst), L.ptr(dst_t), rows, cols)
+    L.check(rc, "s2vt_cast_bf16")
+    return dst, dst_t
+
+
+def lstm_fwd(T, B, H, n_pre, pre, bias_sum, w_bf, out, gates, cells, hT=None, cT=None, h0=None, c0=None):
+    with ops._timed("lstm_fwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 4 * H + 2.0 * T * B * 6 * H):
+        rc = L.load().s2vt_lstm_fwd_bf16(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre), L.ptr(bias_sum), L.ptr(w_bf), L.ptr(h0),
+                                         L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT))
+    L.check(rc, "s2vt_lstm_fwd_bf16")
+
+
+def lstm_bwd(T, B, H, dout_t0, dout, gates, cells, w_t_bf, dgates):
+    with ops._timed("lstm_bwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 3 * H + 2.0 * T * B * 8 * H):
+        rc = L.load().s2vt_lstm_bwd_bf16(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
+                                         L.ptr(w_t_bf), L.ptr(dgates))
+    L.check(rc, "s2vt_lstm_bwd_bf16")
+
+
+def colsum_bf16(X, M, N, ld, out, x_off=0):
+    with ops._timed("colsum_bf16", 0.0, 2.0 * M * N):
+        rc = L.load().s2vt_colsum_bf16(L.stream_ptr(X.device), L.ptr(X, x_off), M, N, ld, L.ptr(out))
+    L.check(rc, "s2vt_colsum_bf16")
+
+
+def ce_bf16(logits, R, V, targets, t_off, tmap, loss=None, dlogits=None, gscale=None):
+    row_loss = torch.empty(R, dtype=torch.float32, device=logits.device) if loss is not None else None
+    with ops._timed("ce_bf16", 0.0, 4.0 * R * V + (2.0 * R * V if dlogits is not None else 0.0)):
+        rc = L.load().s2vt_ce_bf16(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
+                                   L.ptr(loss), L.ptr(dlogits), L.ptr(gscale))
+    L.check(rc, "s2vt_ce_bf16")
+
+
+# ------------------------------------------------------------------------------------------------ bf16 weight shadows
+class ShadowCache:
+    """bf16 mirrors of the fp32 master weights (+ W_hh^T for the BPTT kernels and the summed LSTM biases).  Rebuilt when any
+    parameter's storage / version changes or an Adam kernel ran (ops.WEIGHT_EPOCH)."""
+
+    def __init__(self):
+        self.key = None
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def get(self, P: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        key = (ops.WEIGHT_EPOCH,) + tuple((p.data_ptr(), p._version) for p in P.values())
+        if key == self.key:
+            return self.t
+        t = {}
+        for name in ("feat_linear.weight", "vid_rnn.weight_ih_l0", "word_rnn.weight_ih_l0", "out_linear.weight", "embedding.weight"):
+            w = P[name]
+            t[name], _ = cast(w, w.shape[0], w.shape[1])
+        for name in ("vid_rnn.weight_hh_l0", "word_rnn.weight_hh_l0"):
+            w = P[name]
+            t[name], t[name + ".T"] = cast(w, w.shape[0], w.shape[1], want_t=True)
+        t["b1"] = ops.add_f32(P["vid_rnn.bias_ih_l0"], P["vid_rnn.bias_hh_l0"], torch.empty_like(P["vid_rnn.bias_ih_l0"]))
+        t["b2"] = ops.add_f32(P["word_rnn.bias_ih_l0"], P["word_rnn.bias_hh_l0"], torch.empty_like(P["word_rnn.bias_ih_l0"]))
+        self.key, self.t = key, t
+        return t
+
+
+# ------------------------------------------------------------------------------------------------ forward / backward
+def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool):
+    """S2VT.forward(mode='train') on tensor cores (S2VTModel.py:48-81).  Returns (fp32 logits, saved)."""
+    B, Lq, F = feats.shape
+    H = P["vid_rnn.weight_hh_l0"].shape[1]
+    V, E = P["embedding.weight"].shape
+    T = 2 * Lq - 1
+    dev = feats.device
+    Bp = int(L.load().s2vt_lstm_bf16_batch_pad(B))
+    xb, _ = cast(feats, B * Lq, F)                                               # batch-major rows (b, l)
+    xproj = torch.empty(Lq * B, H, dtype=BF, device=dev)                         # time-major rows (l, b)
+    gemm(B * Lq, H, F, xb, F, False, S["feat_linear.weight"], F, False, xproj, rowmap(Lq, H, B * H), out_bf16=True,
+         bias=P["feat_linear.bias"])
+    pre1 = torch.empty(Lq * B, 4 * H, device=dev)
+    gemm(Lq * B, 4 * H, H, xproj, H, False, S["vid_rnn.weight_ih_l0"], H, False, pre1, dense(4 * H), bias=S["b1"])
+    out1 = torch.empty(T * B, H, dtype=BF, device=dev)
+    g1 = torch.empty(T * Bp * 4 * H, dtype=BF, device=dev) if stash else None
+    c1 = torch.empty(T * Bp * H, device=dev) if stash else None
+    lstm_fwd(T, B, H, Lq, pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1)
+    emb_seq = torch.empty((Lq - 1) * B, E, dtype=BF, device=dev)
+    rc = L.load().s2vt_embed_gather_bf16(L.stream_ptr(dev), L.ptr(S["embedding.weight"]), E, L.ptr(targets), Lq - 1, B, Lq - 1,
+                                         L.ptr(emb_seq), E)
+    L.check(rc, "s2vt_embed_gather_bf16")
+    pre2 = torch.empty(T * B, 4 * H, device=dev)
+    gemm(T * B, 4 * H, H, out1, H, False, S["word_rnn.weight_ih_l0"], E + H, False, pre2, dense(4 * H), bias=S["b2"], b_off=E)
+    gemm((Lq - 1) * B, 4 * H, E, emb_seq, E, False, S["word_rnn.weight_ih_l0"], E + H, False, pre2, dense(4 * H), accumulate=True,
+         c_off=Lq * B * 4 * H)
+    out2 = torch.empty(T * B, H, dtype=BF, device=dev)
+    g2 = torch.empty(T * Bp * 4 * H, dtype=BF, device=dev) if stash else None
+    c2 = torch.empty(T * Bp * H, device=dev) if stash else None
+    lstm_fwd(T, B, H, T, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2)
+    R = (Lq - 1) * B
+    if batch_major_logits:
+        logits = torch.empty(B, Lq - 1, V, device=dev)
+        cmap = rowmap(B, V, (Lq - 1) * V)
+    else:
+        logits = torch.empty(R, V, device=dev)
+        cmap = dense(V)
+    gemm(R, V, H, out2, H, False, S["out_linear.weight"], H, False, logits, cmap, bias=P["out_linear.bias"], a_off=Lq * B * H)
+    saved = dict(xb=xb, xproj=xproj, out1=out1, g1=g1, c1=c1, out2=out2, g2=g2, c2=c2, emb_seq=emb_seq,
+                 dims=(B, Lq, F, H, E, V, T)) if stash else None
+    return logits, saved
+
+
+def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool, gout: Optional[Dict[str, torch.Tensor]] = None,
+                   on_ready=None):
+    """BPTT for train_forward: dl_bf = dL/dlogits as bf16 [(L-1)B, V] in time-major row order.
+    Returns fp32 grads keyed by parameter name (+ 'feats' when requested)."""
+    B, Lq, F, H, E, V, T = saved["dims"]
+    dev = dl_bf.device
+    R = (Lq - 1) * B
+    out1, out2, xproj = saved["out1"], saved["out2"], saved["xproj"]
+    G = {}
+
+    def _new(name, *shape):
+        return gout[name] if gout is not None else torch.empty(*shape, device=dev)
+
+    def _ready(bucket):
+        if on_ready is not None:
+            on_ready(bucket)
+
+    hdec = Lq * B * H
+    # ---- out_linear:  dW = dl^T h,  db = colsum(dl),  dh = dl W
+    gW = _new("out_linear.weight", V, H)
+    gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec)
+    gb = _new("out_linear.bias", V)
+    colsum_bf16(dl_bf, R, V, V, gb)
+    G["out_linear.weight"], G["out_linear.bias"] = gW, gb
+    _ready("out_linear")
+    dout2 = torch.empty(T * B, H, device=dev)                                   # rows < L*B never read (dout_t0 = L)
+    gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
+    # ---- word_rnn
+    dg2 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
+    lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
+    gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
+    gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E)
+    gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H)
+    gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
+    gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H)
+    gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
+    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2)
+    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2b)
+    G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
+    _ready("word_rnn")
+    dout1 = torch.empty(T * B, H, device=dev)
+    gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
+    demb = torch.empty(R, E, device=dev)
+    gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H)
+    gE = _new("embedding.weight", V, E)
+    gE.zero_()
+    ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
+    G["embedding.weight"] = gE
+    _ready("embedding")
+    # ---- vid_rnn
+    dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
+    lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
+    gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
+    gemm(4 * H, H, Lq * B, dg1, 4 * H, True, xproj, H, True, gWih1, dense(H))
+    gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)
+    gemm(4 * H, H, (T - 1) * B, dg1, 4 * H, True, out1, H, True, gWhh1, dense(H), a_off=B * 4 * H)
+    gb1, gb1b = _new("vid_rnn.bias_ih_l0", 4 * H), _new("vid_rnn.bias_hh_l0", 4 * H)
+    colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1)
+    colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1b)
+    G.update({"vid_rnn.weight_ih_l0": gWih1, "vid_rnn.weight_hh_l0": gWhh1, "vid_rnn.bias_ih_l0": gb1, "vid_rnn.bias_hh_l0": gb1b})
+    _ready("vid_rnn")
+    # ---- feat_linear: d xproj written back in batch-major row order so that it lines up with the bf16 features
+    dxp = torch.empty(B * Lq, H, dtype=BF, device=dev)
+    gemm(Lq * B, H, 4 * H, dg1, 4 * H, False, S["vid_rnn.weight_ih_l0"], H, True, dxp, rowmap(B, H, Lq * H), out_bf16=True)
+    gWf = _new("feat_linear.weight", H, F)
+    gemm(H, F, B * Lq, dxp, H, True, saved["xb"], F, True, gWf, dense(F))
+    gbf = _new("feat_linear.bias", H)
+    colsum_bf16(dxp, B * Lq, H, H, gbf)
+    G.update({"feat_linear.weight": gWf, "feat_linear.bias": gbf})
+    _ready("feat_linear")
+    if need_dfeats:                                                              # dataloader.py:38 makes feats require grad
+        dfeats = torch.empty(B, Lq, F, device=dev)
+        gemm(B * Lq, F, H, dxp, H, False, S["feat_linear.weight"], F, True, dfeats, dense(F))
+        G["feats"] = dfeats
+    return G

@@ -17,6 +17,7 @@ from typing import Dict, List, Optional
 import torch
 from torch import nn
 
+from . import engine_bf16 as EB
 from . import ops
 from .lib import dense, rowmap, require_cuda
 
@@ -298,10 +299,16 @@ class _TrainLossFn(torch.autograd.Function):
         V = P["embedding.weight"].shape[0]
         need = any(ctx.needs_input_grad)
         tin = targets_full[:, :-1].contiguous()
-        logits, saved = train_forward_f32(P, feats, tin, stash=need, batch_major_logits=False)
+        ctx.bf16 = module._use_bf16()
         loss = torch.empty((), device=feats.device)
         # row (t,b) of the time-major logits is scored against targets_full[b, t+1]
-        ops.ce_f32(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss)
+        if ctx.bf16:
+            ctx.S = module._shadow.get(P)
+            logits, saved = EB.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False)
+            EB.ce_bf16(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss=loss)
+        else:
+            logits, saved = train_forward_f32(P, feats, tin, stash=need, batch_major_logits=False)
+            ops.ce_f32(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss)
         ctx.saved, ctx.P, ctx.feats, ctx.tin, ctx.tfull, ctx.logits = saved, P, feats, tin, targets_full, logits
         return loss
 
@@ -310,21 +317,51 @@ class _TrainLossFn(torch.autograd.Function):
         B, L, _ = ctx.feats.shape
         V = ctx.P["embedding.weight"].shape[0]
         logits = ctx.logits
-        scratch = torch.empty((), device=logits.device)
         g = gloss.contiguous().to(torch.float32)
-        ops.ce_f32(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), scratch, dlogits=logits, gscale=g)
         direct, cb = _direct_grad_targets(ctx.module)
-        grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.tin, logits, False, ctx.needs_input_grad[1],
-                                           gout=direct, on_ready=cb)
+        if ctx.bf16:
+            dl = torch.empty((L - 1) * B, V, dtype=torch.bfloat16, device=logits.device)
+            EB.ce_bf16(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), dlogits=dl, gscale=g)
+            G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
+            grads, dfeats = [G[k] for k in PARAM_ORDER], G.get("feats")
+        else:
+            scratch = torch.empty((), device=logits.device)
+            ops.ce_f32(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), scratch, dlogits=logits, gscale=g)
+            grads, dfeats = train_backward_f32(ctx.P, ctx.saved, ctx.feats, ctx.tin, logits, False, ctx.needs_input_grad[1],
+                                               gout=direct, on_ready=cb)
         ctx.saved = ctx.logits = None
         return (None, dfeats, None) + _finish_grads(ctx.module, direct, grads)
+
+
+class _TrainLogitsBf16Fn(torch.autograd.Function):
+    """forward(mode='train') on tensor cores -> materialised fp32 logits [B,L-1,V] (the API contract); backward receives
+    dL/dlogits from autograd (e.g. from MaskCriterion), casts it to bf16 in time-major order and runs the bf16 BPTT."""
+
+    @staticmethod
+    def forward(ctx, module, feats, targets, *params):
+        P = dict(zip(PARAM_ORDER, params))
+        need = any(ctx.needs_input_grad)
+        ctx.S = module._shadow.get(P)
+        logits, saved = EB.train_forward(P, ctx.S, feats, targets, stash=need, batch_major_logits=True)
+        ctx.saved, ctx.P, ctx.targets, ctx.module = saved, P, targets, module
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        B, Lm1, V = dl.shape
+        # [B, L-1, V] f32 -> time-major [(L-1)B, V] bf16 (layout glue for the caller-supplied gradient)
+        dl_tm = dl.transpose(0, 1).contiguous().view(Lm1 * B, V).to(torch.bfloat16)
+        direct, cb = _direct_grad_targets(ctx.module)
+        G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
+        ctx.saved = None
+        return (None, G.get("feats"), None) + _finish_grads(ctx.module, direct, [G[k] for k in PARAM_ORDER])
 
 
 # --------------------------------------------------------------------------- the module
 class S2VT(nn.Module):
     def __init__(self, vocab_size, feat_dim, length, dim_hid=500, dim_embed=500, feat_dropout=0, rnn_dropout=0,
                  out_dropout=0, num_layers=1, bidirectional=False, rnn_type='lstm', sos_ix=3, eos_ix=4,
-                 train_precision: str = "fp32", decode_precision: str = "fp32"):
+                 train_precision: str = "auto", decode_precision: str = "fp32"):
         super().__init__()
         if str(rnn_type).lower() != 'lstm':
             raise NotImplementedError("only rnn_type='lstm' is supported (the reference warns against GRU, train.py:35)")
@@ -351,6 +388,27 @@ class S2VT(nn.Module):
         self.beam_topk = 20                     # S2VTModel.py:216
         self._grad_views = None                 # set by FusedAdam.attach(): backward writes gradients in place
         self._on_bucket_ready = None
+        self._shadow = EB.ShadowCache()         # bf16 mirrors of the weights (derived, rebuilt lazily, never saved)
+
+    def __getstate__(self):
+        st = self.__dict__.copy()               # whole-module pickles (train.py:167) carry parameters only
+        st["_grad_views"], st["_on_bucket_ready"], st["_shadow"] = None, None, EB.ShadowCache()
+        return st
+
+    def _use_bf16(self) -> bool:
+        """train_precision: 'bf16' = tensor cores (raises if the shapes are unsupported), 'fp32' = exact CUDA-core path,
+        'auto' = bf16 whenever the shapes allow it."""
+        ok = EB.supported(self.dim_hid, self.dim_embed, self.feat_dim, self.vocab_size)
+        if self.train_precision == "bf16":
+            if not ok:
+                raise NotImplementedError("train_precision='bf16' needs dim_hid % 128 == 0, dim_hid <= 512 and dim_embed, feat_dim, "
+                                          "vocab_size multiples of 8; use train_precision='fp32' for other shapes")
+            return True
+        if self.train_precision == "fp32":
+            return False
+        if self.train_precision == "auto":
+            return ok
+        raise ValueError("train_precision must be 'auto', 'bf16' or 'fp32'")
 
     # ---- helpers
     def _params(self) -> Dict[str, torch.Tensor]:
@@ -383,7 +441,8 @@ class S2VT(nn.Module):
                                    "(S2VTModel.py:73-75)" % (feats.shape[0], self.length - 1, tuple(targets.shape)))
             targets = targets.contiguous().to(torch.int64)
             P = self._params()
-            return _TrainLogitsFn.apply(self, feats, targets, *[P[k] for k in PARAM_ORDER])
+            fn = _TrainLogitsBf16Fn if self._use_bf16() else _TrainLogitsFn
+            return fn.apply(self, feats, targets, *[P[k] for k in PARAM_ORDER])
         elif mode == 'test':
             with torch.no_grad():
                 return self._greedy(feats.detach())

@@ -16,6 +16,7 @@ from .lib import RowMap, dense, rowmap
 # ---------------------------------------------------------------------------------------------------------
 # Optional per-call timing (bench.py's roofline leg): CUDA events on the launching stream around each C call.
 _PROFILE = None
+WEIGHT_EPOCH = 0          # bumped whenever an Adam kernel rewrites weights behind autograd's back (bf16 shadows key on it)
 
 
 class profile:
@@ -148,6 +149,8 @@ def ce_f32(logits: torch.Tensor, R: int, V: int, targets: torch.Tensor, t_off: i
 
 def adam_f32(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1: float, beta2: float,
              eps: float, step: int, grad_scale: float = 1.0, bf16_copy: Optional[torch.Tensor] = None) -> None:
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
     L.require_cuda(p, g, m, v)
     with _timed("adam_f32", 0.0, 28.0 * p.numel()):
         rc = L.load().s2vt_adam_f32(L.stream_ptr(p.device), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, beta1, beta2, eps,

@@ -26,6 +26,7 @@ def dev():
 
 
 def build_model(c, P, dev, **kw):
+    kw.setdefault("train_precision", "fp32")          # this file checks the exact path; bf16 parity lives in test_gpu_bf16.py
     m = s2vt_b200.S2VT(c["V"], c["F"], c["L"], dim_hid=c["H"], dim_embed=c["E"], sos_ix=3, eos_ix=4, **kw)
     m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in P.items()}, strict=True)
     return m.to(dev)
