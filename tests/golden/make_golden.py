@@ -91,6 +91,8 @@ def run_case(name, c):
         for k, v in grads.items():
             out["grad_sample/" + k] = sample(v)
             out["grad_norm/" + k] = np.float64(np.linalg.norm(v.astype(np.float64)))
+            if v.size <= 20000:                              # biases: keep the whole vector
+                out["grad_full/" + k] = v
     # one Adam step (train.py:125) on the full-tensor cases: updated params
     if c["full"]:
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)

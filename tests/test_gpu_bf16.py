@@ -228,8 +228,10 @@ def test_bf16_train_step_vs_reference_golden(dev):
     grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
     grads["feats"] = tf.grad.cpu().numpy()
     for k, gv in grads.items():
-        rs = g["grad_sample/" + k]
-        gs = gv.reshape(-1)[::997]
+        if "grad_full/" + k in g:
+            rs, gs = g["grad_full/" + k].reshape(-1), gv.reshape(-1)
+        else:
+            rs, gs = g["grad_sample/" + k], gv.reshape(-1)[::997]
         rel = np.linalg.norm(gs.astype(np.float64) - rs) / max(1e-30, np.linalg.norm(rs.astype(np.float64)))
         n = np.linalg.norm(gv.astype(np.float64))
         nrel = abs(n - float(g["grad_norm/" + k])) / float(g["grad_norm/" + k])
