@@ -194,12 +194,14 @@ int s2vt_beam_search_f32(void* stream, int B, int H, int E, int V, int beam_widt
  * bf16 twin of s2vt_embed_gather_f32 (replaces self.embedding(targets), S2VTModel.py:71). */
 int s2vt_embed_gather_bf16(void* stream, const void* table_bf16, int E, const int64_t* ids, int64_t ids_ld,
                            int B, int n_t, void* out_bf16, int64_t out_ld);
-/* out[n] = sum_m X[m*ld + n] for a bf16 matrix, fp32 accumulation (bias gradients). */
-int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t ld, float* out);
-/* Mean cross entropy as s2vt_ce_f32, with the gradient written as bf16 (the operand dtype of the backward GEMMs).
- * row_loss / loss may be NULL when only dlogits are wanted. */
+/* out[n] = sum_m X[m*ld + n] for a bf16 matrix, fp32 accumulation (bias gradients); out2 (nullable) receives the same
+ * sums (nn.LSTM's b_ih and b_hh share one gradient). */
+int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t ld, float* out, float* out2);
+/* Mean cross entropy as s2vt_ce_f32, single pass over each row (online max / sum-exp), with the gradient written as bf16
+ * (the operand dtype of the backward GEMMs).  row_lse [R] (nullable) stashes each row's log-sum-exp in the forward call;
+ * a backward call passes it back with have_lse = 1 and reads every logit exactly once.  row_loss / loss may be NULL. */
 int s2vt_ce_bf16(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
-                 float* row_loss, float* loss, void* dlogits_bf16, const float* gscale);
+                 float* row_loss, float* loss, float* row_lse, int have_lse, void* dlogits_bf16, const float* gscale);
 
 #ifdef __cplusplus
 }

@@ -22,18 +22,32 @@ __global__ void embed_gather_bf16_kernel(const __nv_bfloat16* __restrict__ table
   }
 }
 
-// out[n] = sum_m X[m*ld + n], X bf16, fp32 accumulation.  grid.x = ceil(N/64); block = 32 x 8; each thread owns 2 columns.
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long M, int N, long long ld, float* __restrict__ out) {
+// out[n] += sum_{m in row chunk} X[m*ld + n], X bf16, fp32 accumulation.  grid = (ceil(N/64), row chunks); block = 32 x 8; each
+// thread owns 2 adjacent columns (one 4-byte load per row) and the row chunks combine with one atomicAdd per column.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long M, int N, long long ld, float* __restrict__ out,
+                                   float* __restrict__ out2) {
   __shared__ float sh[8][65];
   const int n = blockIdx.x * 64 + threadIdx.x * 2;
+  const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const long long m0 = (long long)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
   float a0 = 0.f, a1 = 0.f;
   if (n + 1 < N && (ld & 1) == 0) {
-    for (long long m = threadIdx.y; m < M; m += 8) {
-      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(X + m * ld + n);
+    const __nv_bfloat16* src = X + n;
+    long long m = m0 + threadIdx.y;
+    for (; m + 24 < m1; m += 32) {                      // 4 independent loads in flight per thread
+      const __nv_bfloat162 v0 = *reinterpret_cast<const __nv_bfloat162*>(src + m * ld);
+      const __nv_bfloat162 v1 = *reinterpret_cast<const __nv_bfloat162*>(src + (m + 8) * ld);
+      const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(src + (m + 16) * ld);
+      const __nv_bfloat162 v3 = *reinterpret_cast<const __nv_bfloat162*>(src + (m + 24) * ld);
+      a0 += (__low2float(v0) + __low2float(v1)) + (__low2float(v2) + __low2float(v3));
+      a1 += (__high2float(v0) + __high2float(v1)) + (__high2float(v2) + __high2float(v3));
+    }
+    for (; m < m1; m += 8) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + m * ld);
       a0 += __low2float(v); a1 += __high2float(v);
     }
   } else if (n < N) {
-    for (long long m = threadIdx.y; m < M; m += 8) {
+    for (long long m = m0 + threadIdx.y; m < m1; m += 8) {
       a0 += __bfloat162float(X[m * ld + n]);
       if (n + 1 < N) a1 += __bfloat162float(X[m * ld + n + 1]);
     }
@@ -48,7 +62,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long lon
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x * 2 + k];
-        out[n + k] = s;
+        atomicAdd(out + n + k, s);
+        if (out2) atomicAdd(out2 + n + k, s);
       }
     }
   }
@@ -75,31 +90,57 @@ __device__ __forceinline__ float blk_reduce_sum(float v, float* sh) {
   return r;
 }
 
-// one CTA per row: row_loss = lse - z[target]; optional bf16 dlogits = (softmax - onehot) * gscale / R
+// one CTA per row.  Pass 1 (skipped when the row's log-sum-exp is supplied): online max / sum-exp in ONE read of the row;
+// row_loss = lse - z[target].  Pass 2 (optional): bf16 dlogits = (softmax - onehot) * gscale / R.
 __global__ void ce_row_bf16_kernel(const float* __restrict__ logits, int V, const int64_t* __restrict__ targets, RowMap tmap,
-                                   float* __restrict__ row_loss, __nv_bfloat16* __restrict__ dlogits, const float* __restrict__ gscale,
-                                   float inv_rows) {
+                                   float* __restrict__ row_loss, float* __restrict__ row_lse, int have_lse,
+                                   __nv_bfloat16* __restrict__ dlogits, const float* __restrict__ gscale, float inv_rows) {
   __shared__ float sh[32];
   const long long r = blockIdx.x;
   const float* z = logits + r * V;
-  float mx = -INFINITY;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, z[j]);
-  mx = blk_reduce_max(mx, sh);
-  float s = 0.f;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) s += __expf(z[j] - mx);
-  s = blk_reduce_sum(s, sh);
-  const float lse = mx + logf(s);
+  float lse;
+  if (have_lse) {
+    lse = row_lse[r];
+  } else {
+    float mx = -INFINITY, s = 0.f;
+    if ((V & 3) == 0) {
+      const float4* z4 = reinterpret_cast<const float4*>(z);
+      for (int j = threadIdx.x; j < V / 4; j += blockDim.x) {
+        const float4 v = z4[j];
+        const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (m4 > mx) { s *= __expf(mx - m4); mx = m4; }
+        s += (__expf(v.x - mx) + __expf(v.y - mx)) + (__expf(v.z - mx) + __expf(v.w - mx));
+      }
+    } else {
+      for (int j = threadIdx.x; j < V; j += blockDim.x) {
+        const float v = z[j];
+        if (v > mx) { s *= __expf(mx - v); mx = v; }
+        s += __expf(v - mx);
+      }
+    }
+    const float gmx = blk_reduce_max(mx, sh);
+    s = (mx == -INFINITY) ? 0.f : s * __expf(mx - gmx);
+    s = blk_reduce_sum(s, sh);
+    lse = gmx + logf(s);
+    if (threadIdx.x == 0 && row_lse) row_lse[r] = lse;
+  }
   const long long tgt = targets[tmap(r)];
   if (threadIdx.x == 0 && row_loss) row_loss[r] = lse - z[tgt];
   if (dlogits) {
     const float sc = (gscale ? gscale[0] : 1.f) * inv_rows;
     __nv_bfloat16* d = dlogits + r * V;
-    if ((V & 1) == 0) {
-      for (int j = threadIdx.x * 2; j < V; j += blockDim.x * 2) {
-        float p0 = __expf(z[j] - lse), p1 = __expf(z[j + 1] - lse);
-        if (j == tgt) p0 -= 1.f;
-        if (j + 1 == tgt) p1 -= 1.f;
-        *reinterpret_cast<__nv_bfloat162*>(d + j) = __floats2bfloat162_rn(p0 * sc, p1 * sc);
+    if ((V & 3) == 0) {
+      const float4* z4 = reinterpret_cast<const float4*>(z);
+      for (int j = threadIdx.x; j < V / 4; j += blockDim.x) {
+        const float4 v = z4[j];
+        float p0 = __expf(v.x - lse), p1 = __expf(v.y - lse), p2 = __expf(v.z - lse), p3 = __expf(v.w - lse);
+        const long long j0 = 4ll * j;
+        if (tgt >= j0 && tgt < j0 + 4) { if (tgt == j0) p0 -= 1.f; else if (tgt == j0 + 1) p1 -= 1.f; else if (tgt == j0 + 2) p2 -= 1.f; else p3 -= 1.f; }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(p0 * sc, p1 * sc), hi = __floats2bfloat162_rn(p2 * sc, p3 * sc);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(d + j0) = pk;
       }
     } else {
       for (int j = threadIdx.x; j < V; j += blockDim.x) {
@@ -138,22 +179,31 @@ extern "C" int s2vt_embed_gather_bf16(void* stream, const void* table_bf16, int 
   return 0;
 }
 
-extern "C" int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t ld, float* out) {
+extern "C" int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t ld, float* out, float* out2) {
   S2VT_REQUIRE(X_bf16 && out, "s2vt_colsum_bf16: null pointer");
   if (N == 0) return 0;
-  colsum_bf16_kernel<<<ceil_div(N, 64), dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X_bf16, M, N, ld, out);
+  cudaStream_t st = (cudaStream_t)stream;
+  S2VT_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+  if (out2) S2VT_CHECK_CUDA(cudaMemsetAsync(out2, 0, sizeof(float) * N, st));
+  const int gx = ceil_div(N, 64);
+  int gy = ceil_div(148 * 8, gx);                       // ~8 CTAs per SM in total
+  const int max_gy = ceil_div(M, 64);
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  colsum_bf16_kernel<<<dim3(gx, gy), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)X_bf16, M, N, ld, out, out2);
   S2VT_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int s2vt_ce_bf16(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
-                            float* row_loss, float* loss, void* dlogits_bf16, const float* gscale) {
+                            float* row_loss, float* loss, float* row_lse, int have_lse, void* dlogits_bf16, const float* gscale) {
   S2VT_REQUIRE(logits && targets, "s2vt_ce_bf16: null pointer");
   S2VT_REQUIRE(R > 0 && V > 0, "s2vt_ce_bf16: empty input");
   S2VT_REQUIRE(!loss || row_loss, "s2vt_ce_bf16: loss needs row_loss scratch");
+  S2VT_REQUIRE(!have_lse || row_lse, "s2vt_ce_bf16: have_lse needs row_lse");
   cudaStream_t st = (cudaStream_t)stream;
-  ce_row_bf16_kernel<<<(unsigned)R, 256, 0, st>>>(logits, V, targets, to_rowmap(tmap), row_loss, (__nv_bfloat16*)dlogits_bf16, gscale,
-                                                 1.0f / (float)R);
+  ce_row_bf16_kernel<<<(unsigned)R, 256, 0, st>>>(logits, V, targets, to_rowmap(tmap), row_loss, row_lse, have_lse,
+                                                 (__nv_bfloat16*)dlogits_bf16, gscale, 1.0f / (float)R);
   S2VT_CHECK_LAUNCH();
   if (loss) {
     mean_f32_kernel<<<1, 256, 0, st>>>(row_loss, R, loss);

@@ -54,17 +54,17 @@ def lstm_bwd(T, B, H, dout_t0, dout, gates, cells, w_t_bf, dgates):
     L.check(rc, "s2vt_lstm_bwd_bf16")
 
 
-def colsum_bf16(X, M, N, ld, out, x_off=0):
+def colsum_bf16(X, M, N, ld, out, out2=None, x_off=0):
     with ops._timed("colsum_bf16", 0.0, 2.0 * M * N):
-        rc = L.load().s2vt_colsum_bf16(L.stream_ptr(X.device), L.ptr(X, x_off), M, N, ld, L.ptr(out))
+        rc = L.load().s2vt_colsum_bf16(L.stream_ptr(X.device), L.ptr(X, x_off), M, N, ld, L.ptr(out), L.ptr(out2))
     L.check(rc, "s2vt_colsum_bf16")
 
 
-def ce_bf16(logits, R, V, targets, t_off, tmap, loss=None, dlogits=None, gscale=None):
+def ce_bf16(logits, R, V, targets, t_off, tmap, loss=None, dlogits=None, gscale=None, row_lse=None, have_lse=False):
     row_loss = torch.empty(R, dtype=torch.float32, device=logits.device) if loss is not None else None
     with ops._timed("ce_bf16", 0.0, 4.0 * R * V + (2.0 * R * V if dlogits is not None else 0.0)):
         rc = L.load().s2vt_ce_bf16(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
-                                   L.ptr(loss), L.ptr(dlogits), L.ptr(gscale))
+                                   L.ptr(loss), L.ptr(row_lse), int(have_lse), L.ptr(dlogits), L.ptr(gscale))
     L.check(rc, "s2vt_ce_bf16")
 
 
@@ -174,8 +174,7 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
     gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H)
     gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
-    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2)
-    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2b)
+    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
     G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
     _ready("word_rnn")
     dout1 = torch.empty(T * B, H, device=dev)
@@ -195,8 +194,7 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)
     gemm(4 * H, H, (T - 1) * B, dg1, 4 * H, True, out1, H, True, gWhh1, dense(H), a_off=B * 4 * H)
     gb1, gb1b = _new("vid_rnn.bias_ih_l0", 4 * H), _new("vid_rnn.bias_hh_l0", 4 * H)
-    colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1)
-    colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1b)
+    colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1, gb1b)
     G.update({"vid_rnn.weight_ih_l0": gWih1, "vid_rnn.weight_hh_l0": gWhh1, "vid_rnn.bias_ih_l0": gb1, "vid_rnn.bias_hh_l0": gb1b})
     _ready("vid_rnn")
     # ---- feat_linear: d xproj written back in batch-major row order so that it lines up with the bf16 features

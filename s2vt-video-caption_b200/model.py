@@ -305,7 +305,8 @@ class _TrainLossFn(torch.autograd.Function):
         if ctx.bf16:
             ctx.S = module._shadow.get(P)
             logits, saved = EB.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False)
-            EB.ce_bf16(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss=loss)
+            ctx.lse = torch.empty((L - 1) * B, device=feats.device)
+            EB.ce_bf16(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss=loss, row_lse=ctx.lse)
         else:
             logits, saved = train_forward_f32(P, feats, tin, stash=need, batch_major_logits=False)
             ops.ce_f32(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss)
@@ -321,7 +322,7 @@ class _TrainLossFn(torch.autograd.Function):
         direct, cb = _direct_grad_targets(ctx.module)
         if ctx.bf16:
             dl = torch.empty((L - 1) * B, V, dtype=torch.bfloat16, device=logits.device)
-            EB.ce_bf16(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), dlogits=dl, gscale=g)
+            EB.ce_bf16(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), dlogits=dl, gscale=g, row_lse=ctx.lse, have_lse=True)
             G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
             grads, dfeats = [G[k] for k in PARAM_ORDER], G.get("feats")
         else:
