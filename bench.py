@@ -176,6 +176,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not os.environ.get("S2VT_KEEP_NCCL_DEBUG"):
+            os.environ.pop("NCCL_DEBUG", None)        # NCCL's version banner goes to stdout; rank 0 must print ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     s2vt_b200.load()
     peaks = load_peaks()
