@@ -269,7 +269,16 @@ def main():
     with ops.profile() as prof:
         for i in range(2):
             step(i)
-    summ = prof.summary()
+    detail = prof.summary()
+    summ, gemm_detail = {}, []
+    for tag, (calls, ms, flops, nbytes) in detail.items():       # per-shape GEMM tags fold into one family line
+        base = tag.split("[")[0]
+        c0, m0, f0, b0 = summ.get(base, (0, 0.0, 0.0, 0.0))
+        summ[base] = (c0 + calls, m0 + ms, f0 + flops, b0 + nbytes)
+        if "[" in tag:
+            gemm_detail.append({"shape": tag[tag.index("[") + 1:-1], "us": round(1e3 * ms / calls, 1),
+                                "tflops": round(flops / calls / (ms / calls * 1e-3) / 1e12, 1)})
+    gemm_detail.sort(key=lambda d: -d["us"])
     kernels = []
     tot_ms = sum(v[1] for v in summ.values()) or 1.0
     for tag, (calls, ms, flops, nbytes) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
@@ -300,7 +309,7 @@ def main():
                    "l2_policy": "inputs rotate over 4 device-resident batches (336 MB > 126 MB L2)"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e_value, 2), "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
-        "roofline": roofline, "kernels": kernels,
+        "roofline": roofline, "kernels": kernels, "gemm_detail": gemm_detail,
         "step_tflops": round(world * B * FLOP_PER_VIDEO_TRAIN / (ms_step * 1e-3) / 1e12, 3), "loss": final_loss,
     }
     if world == 1 and rank == 0 and not args.no_cpu_baseline:

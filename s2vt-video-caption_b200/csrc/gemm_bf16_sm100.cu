@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "sm100_err.cuh"
+#include <string.h>
 
 namespace s2vt {
 
@@ -26,11 +27,29 @@ struct GemmBf16Params {
   const float* bias;
   int accumulate;
   int c_vec;
+  int tma_store;   // dense C: stage the tile in swizzled smem and write it with cp.async.bulk.tensor (1) or add it into C with
+                   // cp.reduce.async.bulk.tensor (2: accumulate and split-K)
+  int kb_per_split;
 };
+
+namespace ptx {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+}  // namespace ptx
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 2)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmBf16Params p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmBf16Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
@@ -39,6 +58,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);   // this CTA's slice of K (split-K)
 
   if (warp_idx == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
@@ -64,9 +84,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
         if (!ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1)) { atomicExch(&g_sm100_error, 1); break; }
         const uint32_t fb = ptx::smem_u32(&full_bar[s]);
         const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + A_BYTES;
@@ -89,9 +109,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== MMA issuer (one thread) =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int s = (kb - kb0) % STAGES;
+        const uint32_t ph = ((kb - kb0) / STAGES) & 1;
         if (!ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph)) { atomicExch(&g_sm100_error, 2); break; }
         ptx::tc_fence_after();
         const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + A_BYTES;
@@ -102,7 +122,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                    : ptx::make_smem_desc_sw128(sA + k * 32, 16, 1024);
           const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sB + k * 2048, B_BYTES / 2, 1024)
                                    : ptx::make_smem_desc_sw128(sB + k * 32, 16, 1024);
-          ptx::mma_bf16_ss(tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_bf16_ss(tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));        // frees the smem stage when these MMAs retire
       }
@@ -116,6 +136,63 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (!ok) atomicExch(&g_sm100_error, 3);
     ptx::tc_fence_after();
     const long long crow = (m < p.M) ? p.cm(m) : 0;
+    if (p.tma_store) {
+      // The pipeline stages are idle once the accumulator is complete: reuse them as the staging tile.  Row r of a box is
+      // 128 bytes; its 16-byte chunk j sits at r*128 + ((j ^ (r & 7)) * 16) (the 128B swizzle the C tensor map undoes),
+      // so the 32 lanes of a warp -- 32 different rows -- write conflict-free.
+      const int rrow = e * 32 + lane;
+      const uint32_t row_base = smem_base + (uint32_t)rrow * 128u;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(c * 32), r);
+        ptx::tc_wait_ld();
+        const int n = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias && blockIdx.z == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
+        }
+        if (p.Cf) {                                            // box c: 128 rows x 32 fp32
+          const uint32_t box = row_base + (uint32_t)c * 16384u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(box + (uint32_t)((j ^ (rrow & 7)) * 16)),
+                         "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+        } else {                                               // box c/2: 128 rows x 64 bf16; this pass fills half a row
+          const uint32_t box = row_base + (uint32_t)(c >> 1) * 16384u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), t1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), t3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            const int chunk = (c & 1) * 4 + j;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + (uint32_t)((chunk ^ (rrow & 7)) * 16)),
+                         "r"(*reinterpret_cast<uint32_t*>(&t0)), "r"(*reinterpret_cast<uint32_t*>(&t1)),
+                         "r"(*reinterpret_cast<uint32_t*>(&t2)), "r"(*reinterpret_cast<uint32_t*>(&t3)) : "memory");
+          }
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::epi_bar_sync();
+      if (warp_idx == 4 && ptx::elect_one()) {
+        if (p.Cf) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (n0 + c * 32 < p.N) {
+              if (p.tma_store == 2) ptx::tma_reduce_add_2d(&tmC, smem_base + c * 16384, n0 + c * 32, m0);
+              else ptx::tma_store_2d(&tmC, smem_base + c * 16384, n0 + c * 32, m0);
+            }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (n0 + c * 64 < p.N) ptx::tma_store_2d(&tmC, smem_base + c * 16384, n0 + c * 64, m0);
+        }
+        ptx::bulk_commit();
+        ptx::bulk_wait_read0();                                // smem must stay valid until the stores have read it
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -164,6 +241,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -187,15 +265,21 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 tensor map over a [outer, inner] row-major view with `ld` elements between rows, 128B swizzle
+static int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                         int esize);
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_any(out, base, inner, outer, ld, box_inner, box_outer, 2);
+}
+static int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                         int esize) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return fail("TMA operand must be 16-byte aligned with ld %% 8 == 0 (ld=%llu)", (unsigned long long)ld);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * esize) % 16) return fail("TMA operand must be 16-byte aligned with a 16-byte row pitch (ld=%llu)", (unsigned long long)ld);
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)", (int)r,
@@ -242,12 +326,35 @@ extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,
   p.bias = bias; p.accumulate = accumulate;
   const int vq = out_bf16 ? 8 : 4;
   p.c_vec = aligned16(C) && (p.cm.so % vq == 0) && (p.cm.si % vq == 0);
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  const bool dense_c = p.cm.inner == 1 && p.cm.si == 0 && p.c_vec && p.cm.so >= N;
+  p.tma_store = dense_c ? ((accumulate && !out_bf16) ? 2 : (accumulate ? 0 : 1)) : 0;
+  // split-K when the output has too few tiles to fill the machine (the weight-gradient products: K = time x batch)
+  int splits = 1;
+  const int tiles = ceil_div(N, BN) * ceil_div(M, BM);
+  if (dense_c && !out_bf16 && tiles < 148 && p.num_kb >= 16) {
+    splits = 296 / tiles;
+    if (splits > 8) splits = 8;
+    if (splits > p.num_kb / 8) splits = p.num_kb / 8;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);                 // no empty slices
+  if (splits > 1) {
+    if (!accumulate) S2VT_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)p.cm.so * 4, 0, (size_t)N * 4, (size_t)M, (cudaStream_t)stream));
+    p.tma_store = 2;
+  }
+  if (p.tma_store) {
+    rc = make_tmap_any(&tmC, C, (uint64_t)N, (uint64_t)M, (uint64_t)p.cm.so, out_bf16 ? 64 : 32, 128, out_bf16 ? 2 : 4);
+    if (rc) return rc;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), splits);
   cudaStream_t st = (cudaStream_t)stream;
 #define S2VT_LAUNCH_GEMM(AM, BMJ)                                                                                   \
   do {                                                                                                              \
     S2VT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
-    gemm_bf16_kernel<AM, BMJ><<<grid, 256, GEMM_SMEM, st>>>(tmA, tmB, p);                                           \
+    gemm_bf16_kernel<AM, BMJ><<<grid, 256, GEMM_SMEM, st>>>(tmA, tmB, tmC, p);                                        \
   } while (0)
   if (!a_mn_major && !b_mn_major) S2VT_LAUNCH_GEMM(false, false);
   else if (a_mn_major && !b_mn_major) S2VT_LAUNCH_GEMM(true, false);

@@ -25,7 +25,8 @@ def supported(H: int, E: int, F: int, V: int) -> bool:
 
 # ------------------------------------------------------------------------------------------------ thin wrappers
 def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None, accumulate=False, a_off=0, b_off=0, c_off=0):
-    with ops._timed("gemm_bf16", 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if out_bf16 else 4.0) * M * N):
+    tag = "gemm_bf16[%dx%dx%d %s%s%s]" % (M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", " bf16out" if out_bf16 else "")
+    with ops._timed(tag, 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if out_bf16 else 4.0) * M * N):
         rc = L.load().s2vt_gemm_bf16(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), lda, int(a_mn), L.ptr(B, b_off), ldb, int(b_mn),
                                      L.ptr(C, c_off), cmap, int(out_bf16), L.ptr(bias), int(accumulate))
     L.check(rc, "s2vt_gemm_bf16")
