@@ -382,8 +382,11 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
 template <int NB, bool W_TMEM>
 static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFwdParams& p) {
   const int H = p.H, CS = H / 32;
-  const size_t smem = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + 2 * (size_t)NB * H * 2 + 2 * (size_t)4 * NB * 32 * 4 +
+  const size_t smem_need = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + 2 * (size_t)NB * H * 2 + 2 * (size_t)4 * NB * 32 * 4 +
                       2 * (size_t)NB * 32 * 4 * 2 + 4 * 256;
+  // This CTA owns all of the SM's tensor memory (512 columns for H = 512): a co-resident GEMM CTA from another stream would block
+  // in tcgen05.alloc until the sweep ends and would contend for the SM meanwhile.  Asking for > (227 - 97) KB keeps them out.
+  const size_t smem = smem_need < (size_t)136 * 1024 ? (size_t)136 * 1024 : smem_need;
   auto kern = lstm_fwd_cluster_kernel<NB, W_TMEM>;
   S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (CS > 8) S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -264,7 +264,9 @@ extern "C" int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0
   p.dout = dout; p.gates = (const __nv_bfloat16*)gates_bf16; p.cells = cells; p.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
   p.dgates = (__nv_bfloat16*)dgates_bf16;
   const int CS = H / 32;
-  const size_t smem = 1024 + 2 * (size_t)CS * 32 * BWD_NB * 4 + (size_t)BWD_NB * 128 * 2;
+  const size_t smem_need = 1024 + 2 * (size_t)CS * 32 * BWD_NB * 4 + (size_t)BWD_NB * 128 * 2;
+  // keep GEMM CTAs of other streams (97 KB each) off the SMs of the cluster: this CTA owns the SM's tensor memory
+  const size_t smem = smem_need < (size_t)136 * 1024 ? (size_t)136 * 1024 : smem_need;
   auto kern = lstm_bwd_cluster_kernel;
   S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (CS > 8) S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

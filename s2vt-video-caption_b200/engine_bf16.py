@@ -95,6 +95,16 @@ class ShadowCache:
         return t
 
 
+_SIDE = {}
+
+
+def _side_stream(dev) -> torch.cuda.Stream:
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 # ------------------------------------------------------------------------------------------------ forward / backward
 def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool):
     """S2VT.forward(mode='train') on tensor cores (S2VTModel.py:48-81).  Returns (fp32 logits, saved)."""
@@ -157,39 +167,53 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
             on_ready(bucket)
 
     hdec = Lq * B * H
-    # ---- out_linear:  dW = dl^T h,  db = colsum(dl),  dh = dl W
-    gW = _new("out_linear.weight", V, H)
-    gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec)
-    gb = _new("out_linear.bias", V)
-    colsum_bf16(dl_bf, R, V, V, gb)
-    G["out_linear.weight"], G["out_linear.bias"] = gW, gb
-    _ready("out_linear")
+    # The BPTT sweeps occupy 64 of the 148 SMs and form the critical chain  dl -> dout2 -> sweep(word_rnn) -> dout1 ->
+    # sweep(vid_rnn).  Every product that is NOT on that chain (weight / bias / embedding gradients) runs on a side stream,
+    # concurrently with the sweep that follows its inputs.
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    ev_dl = torch.cuda.Event()
+    ev_dl.record(main)
+    # ---- out_linear:  dh = dl W on the chain;  dW = dl^T h,  db = colsum(dl) on the side stream
     dout2 = torch.empty(T * B, H, device=dev)                                   # rows < L*B never read (dout_t0 = L)
     gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
+    gW = _new("out_linear.weight", V, H)
+    gb = _new("out_linear.bias", V)
+    with torch.cuda.stream(side):
+        side.wait_event(ev_dl)
+        gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec)
+        colsum_bf16(dl_bf, R, V, V, gb)
+        G["out_linear.weight"], G["out_linear.bias"] = gW, gb
+        _ready("out_linear")
     # ---- word_rnn
     dg2 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
     lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
-    gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
-    gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E)
-    gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H)
-    gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
-    gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H)
-    gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
-    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
-    G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
-    _ready("word_rnn")
+    ev_dg2 = torch.cuda.Event()
+    ev_dg2.record(main)
     dout1 = torch.empty(T * B, H, device=dev)
     gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
-    demb = torch.empty(R, E, device=dev)
-    gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H)
+    gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
+    gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
+    gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
     gE = _new("embedding.weight", V, E)
-    gE.zero_()
-    ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
-    G["embedding.weight"] = gE
-    _ready("embedding")
+    with torch.cuda.stream(side):
+        side.wait_event(ev_dg2)
+        gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E)
+        gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H)
+        gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H)
+        colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
+        G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
+        _ready("word_rnn")
+        demb = torch.empty(R, E, device=dev)
+        gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H)
+        gE.zero_()
+        ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
+        G["embedding.weight"] = gE
+        _ready("embedding")
     # ---- vid_rnn
     dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
     lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
+    main.wait_stream(side)                                                      # join before the tail (and before grads are used)
     gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
     gemm(4 * H, H, Lq * B, dg1, 4 * H, True, xproj, H, True, gWih1, dense(H))
     gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)
