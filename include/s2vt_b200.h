@@ -137,6 +137,11 @@ int s2vt_embed_gather_f32(void* stream, const float* table, int E, const int64_t
 int s2vt_embed_scatter_add_f32(void* stream, float* grad_table, int E, const int64_t* ids, int64_t ids_ld,
                                int B, int n_t, const float* src, int64_t src_ld);
 
+/* dst[(t*B + b)*N + n] = src[b*src_ld + n] for t < n_t: repeats one [B,N] block over time.
+ * replaces: the per-step re-use of the (constant) attention context and its broadcast gradient,
+ * attention_baseline.py:56,71-77 (torch.bmm of an all-ones weight row + torch.cat per decode step). */
+int s2vt_bcast_rows_f32(void* stream, const float* src, int64_t src_ld, int B, int N, int n_t, float* dst);
+
 /* out[i] = a[i] + b[i]  (b_ih + b_hh) */
 int s2vt_add_f32(void* stream, const float* a, const float* b, float* out, int64_t n);
 

@@ -1,5 +1,6 @@
 """s2vt-video-caption_b200: B200-native (sm_100a) drop-in for the S2VT encoder-decoder hot path of
 Kamino666/S2VT-video-caption.  Import through the `s2vt_b200` shim at the repo root."""
+from .att_model import ATT_PARAM_ORDER, Att_Baseline
 from .criterion import MaskCriterion
 from .lib import LIB_PATH, S2VTLibraryError, launch_count, load
 from .model import PARAM_ORDER, S2VT, S2VTModel
@@ -7,5 +8,5 @@ from .optim import FusedAdam
 
 BF16_TRAIN_READY = True     # bench.py: the tensor-core training path is the default for supported shapes
 
-__all__ = ["BF16_TRAIN_READY", "S2VT", "S2VTModel", "MaskCriterion", "FusedAdam", "PARAM_ORDER", "load", "launch_count", "LIB_PATH",
+__all__ = ["BF16_TRAIN_READY", "S2VT", "S2VTModel", "Att_Baseline", "ATT_PARAM_ORDER", "MaskCriterion", "FusedAdam", "PARAM_ORDER", "load", "launch_count", "LIB_PATH",
            "S2VTLibraryError"]

@@ -69,6 +69,14 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
   if (i < n) out[i] = a[i] + b[i];
 }
 
+// dst[(t*B + b)*N + n] = src[b*src_ld + n]: one [B,N] block repeated over n_t time steps (the constant attention context)
+__global__ void bcast_rows_kernel(const float* __restrict__ src, long long src_ld, int B, int N, float* __restrict__ dst) {
+  const int row = blockIdx.x;                 // t*B + b
+  const float* s = src + (long long)(row % B) * src_ld;
+  float* d = dst + (long long)row * N;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) d[n] = s[n];
+}
+
 // ---------------------------------------------------------------- column sums
 // grid.x = ceil(N/32); block = 32 x 8.  Row chunks are summed in a fixed order -> deterministic.
 __global__ void colsum_kernel(const float* __restrict__ X, long long M, int N, long long ld, float* __restrict__ out, int accumulate) {
@@ -203,6 +211,14 @@ extern "C" int s2vt_embed_scatter_add_f32(void* stream, float* grad_table, int E
   S2VT_REQUIRE(grad_table && ids && src, "s2vt_embed_scatter_add_f32: null pointer");
   if (B * n_t == 0) return 0;
   embed_scatter_add_kernel<<<B * n_t, 128, 0, (cudaStream_t)stream>>>(grad_table, E, ids, ids_ld, B, n_t, src, src_ld);
+  S2VT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int s2vt_bcast_rows_f32(void* stream, const float* src, int64_t src_ld, int B, int N, int n_t, float* dst) {
+  S2VT_REQUIRE(src && dst, "s2vt_bcast_rows_f32: null pointer");
+  if (B * n_t == 0 || N == 0) return 0;
+  bcast_rows_kernel<<<B * n_t, 128, 0, (cudaStream_t)stream>>>(src, src_ld, B, N, dst);
   S2VT_CHECK_LAUNCH();
   return 0;
 }

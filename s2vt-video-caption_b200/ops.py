@@ -83,6 +83,13 @@ def add_f32(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor
     return out
 
 
+def bcast_rows_f32(src: torch.Tensor, src_off: int, src_ld: int, B: int, N: int, n_t: int, dst: torch.Tensor) -> torch.Tensor:
+    _f32(src, "src"); _f32(dst, "dst")
+    L.require_cuda(src, dst)
+    L.check(L.load().s2vt_bcast_rows_f32(L.stream_ptr(src.device), L.ptr(src, src_off), src_ld, B, N, n_t, L.ptr(dst)), "s2vt_bcast_rows_f32")
+    return dst
+
+
 def lstm_fwd_f32(T: int, B: int, H: int, n_pre: int, pre: Optional[torch.Tensor], bias_sum: torch.Tensor, w_hh: torch.Tensor,
                  out: torch.Tensor, gates: Optional[torch.Tensor] = None, cells: Optional[torch.Tensor] = None,
                  h0: Optional[torch.Tensor] = None, c0: Optional[torch.Tensor] = None, hT: Optional[torch.Tensor] = None,

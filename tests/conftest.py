@@ -43,3 +43,16 @@ def golden_inputs(g):
 
 def beam_rows_to_lists(rows):
     return [[int(t) for t in r if t >= 0] for r in rows]
+
+
+def att_golden_inputs(g):
+    """(params, feats, targets, mask, cfg) of an Att_Baseline fixture (tests/golden/make_golden_att.py)."""
+    from oracle import att_numpy as A
+    from oracle import s2vt_numpy as O
+    c = golden_cfg(g)
+    if "feats" in g:
+        P = {k[6:]: g[k] for k in g if k.startswith("param/")}
+        return P, g["feats"], g["targets"], g["mask"], c
+    P = A.synth_params(c["V"], c["F"], c["H"], c["E"], seed=c["wseed"], out_scale=c["out_scale"], ctx_scale=c["ctx_scale"])
+    feats, targets, mask = O.synth_batch(c["B"], c["L"], c["F"], c["V"], seed=c["dseed"], real_tokens=c["real"])
+    return P, feats, targets, mask, c

@@ -103,3 +103,29 @@ def test_product_package_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 assert "oracle" not in open(os.path.join(root, f)).read(), f
+
+
+def test_att_baseline_state_dict_and_seeded_init():
+    """Att_Baseline drop-in: 22 tensors in the reference's registration order (attention_baseline.py:23-33), identical
+    weights from the same seed, padding_idx row zeroed, no CPU fallback."""
+    V, F, Lq, H, E = 30, 20, 4, 8, 6
+    torch.manual_seed(7)
+    m = s2vt_b200.Att_Baseline(V, F, Lq, dim_hid=H, dim_embed=E)
+    torch.manual_seed(7)
+    ref = dict(encoder=torch.nn.LSTM(H, H, batch_first=True, bidirectional=True),
+               decoder=torch.nn.LSTM(2 * H + E, H, batch_first=True), feat_linear=torch.nn.Linear(F, H),
+               embedding=torch.nn.Embedding(V, E, padding_idx=0), out_linear=torch.nn.Linear(H, V),
+               att_enc=torch.nn.Linear(2 * H, H), att_prev_hid=torch.nn.Linear(H, H), att_apply=torch.nn.Linear(H, 1, bias=False))
+    sd = m.state_dict()
+    keys = [n + "." + k for n, mod in ref.items() for k in mod.state_dict()]
+    assert list(sd.keys()) == keys == list(s2vt_b200.ATT_PARAM_ORDER)
+    for n, mod in ref.items():
+        for k, v in mod.state_dict().items():
+            assert torch.equal(sd[n + "." + k], v), n + "." + k
+    assert not sd["embedding.weight"][0].any()
+    for a in ("dim_feat", "length", "dim_hid", "dim_embed", "sos_ix", "eos_ix", "vocab_size"):
+        assert hasattr(m, a)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 4, 20), targets=torch.zeros(2, 3, dtype=torch.int64), mode="train")
+    with pytest.raises(NotImplementedError):
+        s2vt_b200.Att_Baseline(V, F, Lq, feat_dropout=0.1)

@@ -1,0 +1,97 @@
+"""Att_Baseline drop-in (CUDA, through the C ABI, exact fp32 kernels) against golden vectors dumped from the unmodified
+reference class (tests/golden/att_*.npz) and the numpy oracle on fresh inputs.  Tolerances as for S2VT's exact path:
+logits 2e-5 * max(1,|z|max), loss rtol 1e-5, gradients 1e-4 * |g|max, greedy ids bit-exact.  Needs a B200 (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import att_golden_inputs, load_golden
+from oracle import att_numpy as A
+from oracle import s2vt_numpy as O
+
+pytestmark = pytest.mark.gpu
+
+import s2vt_b200  # noqa: E402
+
+STRIDE = 997
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    s2vt_b200.load()
+    return torch.device("cuda:0")
+
+
+def build(c, P, dev):
+    m = s2vt_b200.Att_Baseline(c["V"], c["F"], c["L"], dim_hid=c["H"], dim_embed=c["E"], sos_ix=3, eos_ix=4)
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in P.items()}, strict=True)
+    return m.to(dev)
+
+
+def run_train(model, feats, targets, mask, dev):
+    tf = torch.from_numpy(feats).to(dev).requires_grad_(True)
+    tt = torch.from_numpy(targets).to(dev)
+    logits = model(tf, targets=tt[:, :-1], mode="train")
+    loss = s2vt_b200.MaskCriterion()(logits, tt, torch.from_numpy(mask).to(dev))
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
+    grads["feats"] = tf.grad.cpu().numpy()
+    return logits.detach().cpu().numpy(), loss.item(), grads
+
+
+@pytest.mark.parametrize("name", ["att_tiny", "att_mid"])
+def test_att_train_vs_reference_golden(dev, name):
+    g = load_golden(name)
+    P, feats, targets, mask, c = att_golden_inputs(g)
+    logits, loss, grads = run_train(build(c, P, dev), feats, targets, mask, dev)
+    assert logits.shape == (c["B"], c["L"] - 1, c["V"])
+    assert np.abs(logits - g["logits"]).max() <= 2e-5 * max(1.0, float(np.abs(g["logits"]).max()))
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert set(grads) == set(A.PARAM_NAMES) | {"feats"}
+    for k, gv in grads.items():
+        ref = g["grad/" + k]
+        assert np.abs(gv - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k
+
+
+def test_att_train_msvd_shape_vs_reference_golden(dev):
+    g = load_golden("att_msvd")
+    P, feats, targets, mask, c = att_golden_inputs(g)
+    logits, loss, grads = run_train(build(c, P, dev), feats, targets, mask, dev)
+    ref = g["logits_sample"]
+    assert np.abs(logits.reshape(-1)[::STRIDE] - ref).max() <= 2e-5 * max(1.0, float(np.abs(ref).max()))
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for k, gv in grads.items():
+        ref = g["grad_sample/" + k]
+        tol = 2e-4 * max(np.abs(ref).max(), g["grad_norm/" + k] / np.sqrt(gv.size)) + 1e-9
+        assert np.abs(gv.reshape(-1)[::STRIDE] - ref).max() <= tol, k
+        assert abs(np.linalg.norm(gv.astype(np.float64)) - g["grad_norm/" + k]) <= 2e-4 * g["grad_norm/" + k] + 1e-12, k
+
+
+@pytest.mark.parametrize("name", ["att_tiny", "att_mid", "att_msvd"])
+def test_att_greedy_bit_exact(dev, name):
+    g = load_golden(name)
+    P, feats, targets, mask, c = att_golden_inputs(g)
+    tok = build(c, P, dev)(torch.from_numpy(feats).to(dev), mode="test")
+    assert tok.dtype == torch.int64 and tuple(tok.shape) == (c["B"], c["L"])
+    assert np.array_equal(tok.cpu().numpy(), g["greedy"])
+
+
+def test_att_vs_oracle_fresh_inputs(dev):
+    """Fresh seeded case (odd sizes, batch not a multiple of anything) against the numpy oracle."""
+    V, F, H, E, L, B = 211, 72, 40, 28, 9, 7
+    P = A.synth_params(V, F, H, E, seed=901, out_scale=10.0, ctx_scale=0.3)
+    feats, targets, mask = O.synth_batch(B, L, F, V, seed=902, real_tokens=6)
+    c = dict(V=V, F=F, H=H, E=E, L=L, B=B)
+    logits, loss, grads = run_train(build(c, P, dev), feats, targets, mask, dev)
+    ref_logits, cache = A.forward_train(P, feats, targets[:, :-1], keep=True)
+    ref_grads = A.backward(P, cache, O.dlogits_of_loss(ref_logits, targets))
+    assert np.abs(logits - ref_logits).max() <= 2e-5 * max(1.0, float(np.abs(ref_logits).max()))
+    assert abs(loss - float(O.mask_criterion(ref_logits, targets, mask))) <= 1e-5 * abs(loss)
+    for k, gv in grads.items():
+        assert np.abs(gv - ref_grads[k]).max() <= 1e-4 * np.abs(ref_grads[k]).max() + 1e-7, k
+    pred, margins = A.greedy(P, feats)
+    if margins.min() > 1e-4:
+        tok = build(c, P, dev)(torch.from_numpy(feats).to(dev), mode="test")
+        assert np.array_equal(tok.cpu().numpy(), pred)
