@@ -74,6 +74,10 @@ int s2vt_gemm_bf16(void* stream, int M, int N, int K,
                    void* C, s2vt_rowmap cmap, int out_bf16,
                    const float* bias, int accumulate);
 
+/* Scheduling knobs of s2vt_gemm_bf16 for the calling thread: max_ctas > 0 caps the persistent kernel's grid (used when the
+ * recurrence clusters of another stream hold part of the machine), use_persistent = 0 forces the one-tile-per-CTA kernel. */
+int s2vt_gemm_bf16_set_mode(int max_ctas, int use_persistent);
+
 /* f32 -> bf16 cast (optionally also writes the transpose: dst_t[c, r] = src[r, c]). */
 int s2vt_cast_bf16(void* stream, const float* src, void* dst, void* dst_t, int64_t rows, int64_t cols);
 

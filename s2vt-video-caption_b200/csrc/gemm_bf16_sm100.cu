@@ -265,13 +265,13 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 tensor map over a [outer, inner] row-major view with `ld` elements between rows, 128B swizzle
-static int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
-                         int esize);
+int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                  int esize);
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
   return make_tmap_any(out, base, inner, outer, ld, box_inner, box_outer, 2);
 }
-static int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
-                         int esize) {
+int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                  int esize) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * esize) % 16) return fail("TMA operand must be 16-byte aligned with a 16-byte row pitch (ld=%llu)", (unsigned long long)ld);
@@ -293,12 +293,26 @@ using namespace s2vt;
 
 extern "C" int s2vt_has_tcgen05(void) { return 1; }
 
-namespace s2vt { int lstm_bf16_error_flag(); int lstm_bwd_bf16_error_flag(); }
+namespace s2vt {
+int lstm_bf16_error_flag();
+int lstm_bwd_bf16_error_flag();
+int gemm_persist_error_flag();
+int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                        void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate);
+void gemm_persist_set_max_ctas(int n);
+static thread_local int g_use_persistent = 1;
+}
+
+extern "C" int s2vt_gemm_bf16_set_mode(int max_ctas, int use_persistent) {
+  gemm_persist_set_max_ctas(max_ctas);
+  g_use_persistent = use_persistent;
+  return 0;
+}
 
 extern "C" int s2vt_device_error_flag(void* stream) {
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -2;
-  const int a = read_sm100_error_flag(), b = lstm_bf16_error_flag(), c = lstm_bwd_bf16_error_flag();
-  return a != 0 ? a : (b != 0 ? b : c);
+  const int a = read_sm100_error_flag(), b = lstm_bf16_error_flag(), c = lstm_bwd_bf16_error_flag(), d = gemm_persist_error_flag();
+  return a != 0 ? a : (b != 0 ? b : (c != 0 ? c : d));
 }
 
 extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,
@@ -329,6 +343,10 @@ extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,
   CUtensorMap tmC;
   memset(&tmC, 0, sizeof(tmC));
   const bool dense_c = p.cm.inner == 1 && p.cm.si == 0 && p.c_vec && p.cm.so >= N;
+  if (dense_c && g_use_persistent) {
+    rc = launch_gemm_persist((cudaStream_t)stream, M, N, K, A, lda, a_mn_major, B, ldb, b_mn_major, C, (int64_t)p.cm.so, out_bf16, bias, accumulate);
+    if (rc >= 0) return rc;
+  }
   p.tma_store = dense_c ? ((accumulate && !out_bf16) ? 2 : (accumulate ? 0 : 1)) : 0;
   // split-K when the output has too few tiles to fill the machine (the weight-gradient products: K = time x batch)
   int splits = 1;

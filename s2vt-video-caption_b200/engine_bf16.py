@@ -24,11 +24,21 @@ def supported(H: int, E: int, F: int, V: int) -> bool:
 
 
 # ------------------------------------------------------------------------------------------------ thin wrappers
-def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None, accumulate=False, a_off=0, b_off=0, c_off=0):
+def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None, accumulate=False, a_off=0, b_off=0, c_off=0,
+         short_ctas=False):
+    """short_ctas: use the one-tile-per-CTA kernel.  Required for products that run BESIDE a recurrence sweep: a persistent CTA
+    keeps its SM for the whole product, and the sweep's 16-CTA clusters could not be placed until it retires."""
     tag = "gemm_bf16[%dx%dx%d %s%s%s]" % (M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", " bf16out" if out_bf16 else "")
-    with ops._timed(tag, 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if out_bf16 else 4.0) * M * N):
-        rc = L.load().s2vt_gemm_bf16(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), lda, int(a_mn), L.ptr(B, b_off), ldb, int(b_mn),
-                                     L.ptr(C, c_off), cmap, int(out_bf16), L.ptr(bias), int(accumulate))
+    lib = L.load()
+    if short_ctas:
+        lib.s2vt_gemm_bf16_set_mode(0, 0)
+    try:
+        with ops._timed(tag, 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if out_bf16 else 4.0) * M * N):
+            rc = lib.s2vt_gemm_bf16(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), lda, int(a_mn), L.ptr(B, b_off), ldb, int(b_mn),
+                                    L.ptr(C, c_off), cmap, int(out_bf16), L.ptr(bias), int(accumulate))
+    finally:
+        if short_ctas:
+            lib.s2vt_gemm_bf16_set_mode(0, 1)
     L.check(rc, "s2vt_gemm_bf16")
 
 
@@ -95,14 +105,16 @@ class ShadowCache:
         return t
 
 
-_SIDE = {}
+_CHAIN = {}
 
 
-def _side_stream(dev) -> torch.cuda.Stream:
+def _chain_stream(dev) -> torch.cuda.Stream:
+    """High-priority stream for the serial chain of the backward pass (dgrad product -> BPTT sweep -> dgrad product -> sweep):
+    whenever a chain kernel and an off-chain kernel are both ready, the chain kernel's CTAs are placed first."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=dev)
-    return _SIDE[key]
+    if key not in _CHAIN:
+        _CHAIN[key] = torch.cuda.Stream(device=dev, priority=-1)
+    return _CHAIN[key]
 
 
 # ------------------------------------------------------------------------------------------------ forward / backward
@@ -168,52 +180,53 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
 
     hdec = Lq * B * H
     # The BPTT sweeps occupy 64 of the 148 SMs and form the critical chain  dl -> dout2 -> sweep(word_rnn) -> dout1 ->
-    # sweep(vid_rnn).  Every product that is NOT on that chain (weight / bias / embedding gradients) runs on a side stream,
-    # concurrently with the sweep that follows its inputs.
-    main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
-    ev_dl = torch.cuda.Event()
-    ev_dl.record(main)
-    # ---- out_linear:  dh = dl W on the chain;  dW = dl^T h,  db = colsum(dl) on the side stream
+    # sweep(vid_rnn), which runs on a high-priority stream.  Every product that is NOT on that chain (weight / bias / embedding
+    # gradients) stays on the caller's stream and runs beside the sweep that follows its inputs, on the other 84 SMs.
+    cur = torch.cuda.current_stream(dev)
+    chain = _chain_stream(dev)
+    chain.wait_stream(cur)
     dout2 = torch.empty(T * B, H, device=dev)                                   # rows < L*B never read (dout_t0 = L)
-    gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
+    dg2 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
+    dout1 = torch.empty(T * B, H, device=dev)
+    dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
+    ev_dout2, ev_dg2, ev_dg1 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    with torch.cuda.stream(chain):
+        gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
+        ev_dout2.record(chain)
+        lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
+        ev_dg2.record(chain)
+        gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
+        lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
+        ev_dg1.record(chain)
+    # ---- out_linear:  dW = dl^T h,  db = colsum(dl)   (beside the word_rnn sweep; released together with it)
+    cur.wait_event(ev_dout2)
     gW = _new("out_linear.weight", V, H)
     gb = _new("out_linear.bias", V)
-    with torch.cuda.stream(side):
-        side.wait_event(ev_dl)
-        gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec)
-        colsum_bf16(dl_bf, R, V, V, gb)
-        G["out_linear.weight"], G["out_linear.bias"] = gW, gb
-        _ready("out_linear")
-    # ---- word_rnn
-    dg2 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
-    lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
-    ev_dg2 = torch.cuda.Event()
-    ev_dg2.record(main)
-    dout1 = torch.empty(T * B, H, device=dev)
-    gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
+    gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True)
+    colsum_bf16(dl_bf, R, V, V, gb)
+    G["out_linear.weight"], G["out_linear.bias"] = gW, gb
+    _ready("out_linear")
+    # ---- word_rnn weight / bias / embedding gradients (beside the vid_rnn sweep)
+    cur.wait_event(ev_dg2)
     gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
     gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
     gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
     gE = _new("embedding.weight", V, E)
-    with torch.cuda.stream(side):
-        side.wait_event(ev_dg2)
-        gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E)
-        gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H)
-        gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H)
-        colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
-        G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
-        _ready("word_rnn")
-        demb = torch.empty(R, E, device=dev)
-        gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H)
-        gE.zero_()
-        ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
-        G["embedding.weight"] = gE
-        _ready("embedding")
-    # ---- vid_rnn
-    dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
-    lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
-    main.wait_stream(side)                                                      # join before the tail (and before grads are used)
+    gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E, short_ctas=True)
+    gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H, short_ctas=True)
+    gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H, short_ctas=True)
+    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
+    G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
+    _ready("word_rnn")
+    demb = torch.empty(R, E, device=dev)
+    gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True)
+    gE.zero_()
+    ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
+    G["embedding.weight"] = gE
+    _ready("embedding")
+    # ---- vid_rnn (tail: the machine is free again)
+    cur.wait_event(ev_dg1)
+    cur.wait_stream(chain)
     gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
     gemm(4 * H, H, Lq * B, dg1, 4 * H, True, xproj, H, True, gWih1, dense(H))
     gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)

@@ -38,6 +38,7 @@ SIGNATURES = {
     "s2vt_device_error_flag": (_i, [_vp]),
     "s2vt_gemm_f32": (_i, [_vp, _i, _i, _i, _vp, RowMap, _i, _vp, RowMap, _i, _vp, RowMap, _vp, _i, _i, _i64]),
     "s2vt_gemm_bf16": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, RowMap, _i, _vp, _i]),
+    "s2vt_gemm_bf16_set_mode": (_i, [_i, _i]),
     "s2vt_cast_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i64]),
     "s2vt_lstm_ws_bytes": (_i64, [_i, _i]),
     "s2vt_lstm_fwd_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -103,6 +103,34 @@ def test_gemm_bf16_mn_major(dev, M, N, K, a_mn, b_mn):
     assert err < 2e-3 * (K ** 0.5), err
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(5056, 512, 13000, False, True), (13000, 512, 5056, True, True), (1000, 520, 2048, False, True),
+                                             (136, 260, 1104, True, False)])
+def test_gemm_bf16_persistent_splitk_and_cta_cap(dev, M, N, K, a_mn, b_mn):
+    """The persistent kernel (dense C) with split-K reduce-add, ragged edges, and a capped grid (the setting used while the
+    recurrence clusters hold part of the machine); the one-tile-per-CTA kernel must agree with it."""
+    lib = L.load()
+    outs = []
+    for max_ctas, persistent in ((0, 1), (37, 1), (0, 0)):
+        lib.s2vt_gemm_bf16_set_mode(max_ctas, persistent)
+        try:
+            C, ref = _gemm_bf16(dev, M, N, K, a_mn, b_mn)
+        finally:
+            lib.s2vt_gemm_bf16_set_mode(0, 1)
+        assert (C.double() - ref).abs().max().item() < 2e-3 * (K ** 0.5)
+        outs.append(C)
+    assert (outs[0] - outs[2]).abs().max().item() < 1e-3 * (K ** 0.5)
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-3 * (K ** 0.5)
+
+
+def test_gemm_bf16_persistent_back_to_back_launches(dev):
+    """Many launches reuse the self-resetting scheduler slots; results must stay correct launch after launch."""
+    for i in range(40):
+        C, ref = _gemm_bf16(dev, 384 + 8 * (i % 3), 520, 192, False, False, seed=i)
+        assert (C.double() - ref).abs().max().item() < 2e-3 * (192 ** 0.5), i
+    C, ref = _gemm_bf16(dev, 700, 328, 640, False, False, out_bf16=True)
+    assert (C.double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+
+
 def test_gemm_bf16_epilogues(dev):
     C, ref = _gemm_bf16(dev, 300, 200, 256, False, False, out_bf16=True)
     assert (C.double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
