@@ -8,8 +8,9 @@
 //                         (b) into a 4 KB shared-memory B operand (canonical no-swizzle K-major layout)
 //     partial[j, b] = sum_{r in rows_c} W_hh[r, j] * dgates[b, r]     tcgen05.mma, A = W_hh[rows_c, :]^T resident in TMEM
 //                                                                     (H/128 tiles of M=128 x K=128), fp32 accumulators in TMEM
-//     reduce-scatter: the 32 x 16 fp32 block of partial that belongs to CTA d's units is pushed into d's receive buffer with
-//                     st.async (DSMEM) and completes on d's mbarrier; d sums the 16 blocks at the start of step t-1.
+//     reduce-scatter: the 32 x 16 block of partial that belongs to CTA d's units is rounded to bf16 (the cluster's DSMEM fabric,
+//                     not the tensor pipe, bounds the step: 16 KB per CTA per step instead of 32 KB) and pushed into d's receive
+//                     buffer with st.async, completing on d's mbarrier; d sums the 16 blocks in fp32 at the start of step t-1.
 //
 // As in the forward kernel there is no grid barrier and no global-memory round trip on the critical path.
 #include "common.cuh"
@@ -40,11 +41,11 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
   __shared__ uint32_t tmem_slot;
 
   const int H = p.H, CS = H / 32, NT = H / 128;      // NT = 128-row output tiles of dh
-  const uint32_t RECV_BYTES = (uint32_t)CS * 32u * NB * 4u;
+  const uint32_t RECV_BYTES = (uint32_t)CS * 32u * NB * 2u;        // [src CTA][column half][unit][8 bf16]
   const uint32_t base = (cl::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sRecv0 = base, sB = base + 2 * RECV_BYTES;
   uint8_t* gen = smem_raw + (base - cl::smem_u32(smem_raw));
-  const float4* gRecv0 = reinterpret_cast<const float4*>(gen);
+  const uint2* gRecv0 = reinterpret_cast<const uint2*>(gen);
   uint8_t* gB = gen + 2 * RECV_BYTES;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -59,7 +60,7 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
   if (warp == 4 && ptx::elect_one()) {
     ptx::mbar_init(cl::smem_u32(&recv_full[0]), 1);
     ptx::mbar_init(cl::smem_u32(&recv_full[1]), 1);
-    ptx::mbar_init(cl::smem_u32(&b_ready), 128);
+    ptx::mbar_init(cl::smem_u32(&b_ready), 1);
     ptx::mbar_init(cl::smem_u32(&mma_done), 1);
     ptx::fence_barrier_init();
   }
@@ -160,7 +161,7 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t d = (uint32_t)min(4 * i + warp, CS - 1);
-      dst_recv[i] = cl::mapa(sRecv0, d) + (uint32_t)(((c * 4 + 0) * 32 + lane) * 16);
+      dst_recv[i] = cl::mapa(sRecv0, d) + (uint32_t)(((c * 2 + 0) * 32 + lane) * 16);
       dst_bar[i] = cl::mapa(cl::smem_u32(&recv_full[0]), d);
     }
     const uint32_t bar_stride = cl::smem_u32(&recv_full[1]) - cl::smem_u32(&recv_full[0]);
@@ -176,11 +177,20 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
         ok = ok && ptx::mbar_wait(cl::smem_u32(&recv_full[rb]), rph[rb]);
         rph[rb] ^= 1;
         if (!ok) { atomicExch(&g_sm100_error, 22); break; }
-        const float4* rsrc = gRecv0 + (size_t)rb * (RECV_BYTES / 16) + q * 32 + u;
-        for (int s = 0; s < CS; ++s) {
-          const float4 v = rsrc[s * 128];
-          dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
+        // columns 4q .. 4q+3 of unit u: half (q >> 1) of each source block, 8-byte pair (q & 1) of the unit's 16-byte chunk -- the
+        // sender swapped the two pairs for odd (u >> 3), so a half-warp's 64-bit reads hit 32 different banks
+        const uint2* rsrc = gRecv0 + (size_t)rb * (RECV_BYTES / 8) + ((q >> 1) * 32 + u) * 2 + ((q ^ (u >> 3)) & 1);
+        float acc2[CPT] = {0.f, 0.f, 0.f, 0.f};                  // two independent chains: the 16 loads pipeline instead of serialising
+#pragma unroll 4
+        for (int s = 0; s < CS; s += 2) {
+          const uint2 v = rsrc[s * 128], w = rsrc[(s + 1) * 128];
+          dh[0] += __uint_as_float(v.x << 16); dh[1] += __uint_as_float(v.x & 0xffff0000u);
+          dh[2] += __uint_as_float(v.y << 16); dh[3] += __uint_as_float(v.y & 0xffff0000u);
+          acc2[0] += __uint_as_float(w.x << 16); acc2[1] += __uint_as_float(w.x & 0xffff0000u);
+          acc2[2] += __uint_as_float(w.y << 16); acc2[3] += __uint_as_float(w.y & 0xffff0000u);
         }
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) dh[j] += acc2[j];
       }
       // ---- B. fused gate gradients
       float dgv[CPT][4];
@@ -208,18 +218,15 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
               __float2bfloat16(dgv[j][g]);
       }
       ptx::fence_proxy_async();
-      if (t > 0) ptx::mbar_arrive(cl::smem_u32(&b_ready));
       if (t > 0) load_step(t - 1, false);                       // prefetch the next step's stash / dout
-      cl::named_bar_sync(1, 128);
-      // ---- D. dgates_t to HBM in GEMM layout: 256 chunks of 8 units x 1 column
+      cl::named_bar_sync(1, 128);                               // every thread's operand writes are fenced: ONE arrival releases the MMAs
+      if (t > 0 && threadIdx.x == 0) ptx::mbar_arrive(cl::smem_u32(&b_ready));
+      // ---- D. dgates_t for HBM (GEMM layout): read the 256 chunks of 8 units x 1 column now, store them after the scatter
+      uint4 dgv4[2];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int x = threadIdx.x + 128 * r;
-        const int kblk = x >> 4, b = x & 15;
-        if (b0 + b < p.B) {
-          const uint4 v = *reinterpret_cast<const uint4*>(gB + (kblk * (NB / 8) + b / 8) * 128 + (b % 8) * 16);
-          *reinterpret_cast<uint4*>(p.dgates + ((long long)t * p.B + b0 + b) * 4 * H + (kblk >> 2) * H + 32 * (int)c + 8 * (kblk & 3)) = v;
-        }
+        dgv4[r] = *reinterpret_cast<const uint4*>(gB + ((x >> 4) * (NB / 8) + (x & 15) / 8) * 128 + ((x & 15) % 8) * 16);
       }
       // ---- E. scatter this CTA's partial dh to the owners of each unit
       if (t > 0) {
@@ -227,17 +234,47 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
         if (!ok) { atomicExch(&g_sm100_error, 23); break; }
         ptx::tc_fence_after();
         const uint32_t boff = (uint32_t)(t & 1);
-        for (int i = 0; i < NT; ++i) {
-          uint32_t r[16];
-          ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * NB), r);
-          ptx::tc_wait_ld();
+        const bool swap_pairs = ((lane >> 3) & 1) != 0;
+        auto scatter = [&](int i, const uint32_t (&r)[16]) {
+          uint32_t pk[8];
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq)
-            cl::st_async_16(dst_recv[i] + boff * RECV_BYTES + (uint32_t)(qq * 32 * 16), r[4 * qq], r[4 * qq + 1], r[4 * qq + 2], r[4 * qq + 3],
-                            dst_bar[i] + boff * bar_stride);
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            pk[j] = *reinterpret_cast<const uint32_t*>(&t2);
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t a0 = pk[4 * hh], a1 = pk[4 * hh + 1], a2 = pk[4 * hh + 2], a3 = pk[4 * hh + 3];
+            cl::st_async_16(dst_recv[i] + boff * RECV_BYTES + (uint32_t)(hh * 32 * 16), swap_pairs ? a2 : a0, swap_pairs ? a3 : a1,
+                            swap_pairs ? a0 : a2, swap_pairs ? a1 : a3, dst_bar[i] + boff * bar_stride);
+          }
+        };
+        const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+        if (NT == 4) {                                           // all four tiles in flight behind one wait
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          ptx::tmem_ld_32x16(t_lane, r0);
+          ptx::tmem_ld_32x16(t_lane + NB, r1);
+          ptx::tmem_ld_32x16(t_lane + 2 * NB, r2);
+          ptx::tmem_ld_32x16(t_lane + 3 * NB, r3);
+          ptx::tc_wait_ld();
+          scatter(0, r0); scatter(1, r1); scatter(2, r2); scatter(3, r3);
+        } else {
+          for (int i = 0; i < NT; ++i) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x16(t_lane + (uint32_t)(i * NB), r);
+            ptx::tc_wait_ld();
+            scatter(i, r);
+          }
         }
         ptx::tc_fence_before();
         cl::named_bar_sync(1, 128);                              // B operand / accumulators are free for the next step
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int x = threadIdx.x + 128 * r;
+        const int kblk = x >> 4, b = x & 15;
+        if (b0 + b < p.B)
+          *reinterpret_cast<uint4*>(p.dgates + ((long long)t * p.B + b0 + b) * 4 * H + (kblk >> 2) * H + 32 * (int)c + 8 * (kblk & 3)) = dgv4[r];
       }
     }
   }
@@ -264,7 +301,7 @@ extern "C" int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0
   p.dout = dout; p.gates = (const __nv_bfloat16*)gates_bf16; p.cells = cells; p.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
   p.dgates = (__nv_bfloat16*)dgates_bf16;
   const int CS = H / 32;
-  const size_t smem_need = 1024 + 2 * (size_t)CS * 32 * BWD_NB * 4 + (size_t)BWD_NB * 128 * 2;
+  const size_t smem_need = 1024 + 2 * (size_t)CS * 32 * BWD_NB * 2 + (size_t)BWD_NB * 128 * 2;
   // keep GEMM CTAs of other streams (97 KB each) off the SMs of the cluster: this CTA owns the SM's tensor memory
   const size_t smem = smem_need < (size_t)136 * 1024 ? (size_t)136 * 1024 : smem_need;
   auto kern = lstm_bwd_cluster_kernel;
