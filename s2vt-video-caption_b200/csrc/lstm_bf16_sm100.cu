@@ -4,7 +4,9 @@
 //   cluster = H/32 CTAs (16 for H = 512); CTA c owns hidden units [32c, 32c+32) = 128 gate rows (i,f,g,o x 32)
 //   W_hh slice  [128 rows x H] bf16 : loaded ONCE into TENSOR MEMORY (tcgen05.st, 128 lanes x H/2 columns) and used as the
 //                                     A operand of every step's MMAs -- the weights never touch shared memory again
-//   h_{t-1}^T   [NB batch x H] bf16 : double-buffered in shared memory in the canonical no-swizzle K-major layout (B operand)
+//   h_{t-1}^T   [16 batch x H] bf16 : double-buffered in shared memory in the canonical no-swizzle K-major layout (B operand).
+//                                     NB = 16 real columns per cluster, or NB = 8 ("wide": twice the clusters, half the exchange
+//                                     volume and epilogue work per step; the MMA still runs N = 16 with 8 idle columns)
 //   per step:   gates[128 x NB] = W_slice . h_{t-1}^T      tcgen05.mma (A in TMEM) M=128 N=NB K=16, fp32 accumulator in TMEM
 //               epilogue warps: tcgen05.ld -> + input-side pre-activation (prefetched one step ahead) -> one MUFU.TANH per gate
 //               -> gate exchange through smem -> c,h update (c stays in registers for the whole sequence)
@@ -78,7 +80,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 }  // namespace ptx
 
-constexpr int LSTM_NB = 16;                 // batch columns per cluster (tcgen05 M=128 needs N % 16 == 0)
+constexpr int LSTM_NB = 16;                 // batch columns per cluster of the stash layout and of the narrow kernel
+constexpr int LSTM_MN = 16;                 // MMA N (tcgen05 M=128 needs N % 16 == 0)
 
 struct LstmFwdParams {
   int T, B, H, n_pre;
@@ -98,6 +101,7 @@ struct LstmFwdParams {
 constexpr int TRACE_STEPS = 32, TRACE_T0 = 16;
 __device__ long long g_lstm_trace[TRACE_STEPS * 8];
 static bool g_trace_enabled = false;
+static int g_last_max_clusters[2] = {-1, -1};   // [wide, narrow] result of cudaOccupancyMaxActiveClusters (debug)
 static int g_dbg_flags = 0;                 // 8 = keep W in shared memory (the v1 data path) instead of TMEM
 #define S2VT_TRACE(slot)                                                                              \
   do {                                                                                                \
@@ -108,16 +112,20 @@ static int g_dbg_flags = 0;                 // 8 = keep W in shared memory (the 
 template <int NB, bool W_TMEM>
 __global__ void __launch_bounds__(160, 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdParams p) {
-  static_assert(NB == 16, "thread mapping below assumes 16 batch columns per cluster (4 per epilogue warp)");
+  static_assert(NB == 16 || NB == 8, "thread mapping below assumes 16 or 8 batch columns per cluster (4 or 2 per epilogue warp)");
+  constexpr int MN = LSTM_MN;
   constexpr int CPT = NB / 4;                       // phase-2 columns per thread
-  constexpr uint32_t LBO_H = (NB / 8) * 128;        // K-direction stride between 8x16B core matrices of h^T
-  constexpr uint32_t SLICE_BYTES = 4 * LBO_H;       // one CTA's 32 hidden units x NB batch, bf16
+  constexpr int NCH = NB;                           // 16-byte h chunks (8 units x 1 column) produced per warp and step
+  constexpr int PPL = NCH / 2;                      // peers each lane serves: 32 / NCH lanes share a chunk and split the 16 peers
+  constexpr uint32_t LBO_H = (MN / 8) * 128;        // K-direction stride between 8x16B core matrices of h^T
+  constexpr uint32_t SLICE_BYTES = 4 * LBO_H;       // one CTA's 32 hidden units x MN batch columns, bf16
+  constexpr uint32_t XCHG_BYTES = 4 * (NB / 8) * 128;   // bytes of it that carry real columns and are exchanged
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full, h_full[2], mma_done;
   __shared__ uint32_t tmem_slot;
 
   const int H = p.H, KC = H / 64, CS = H / 32;
-  const uint32_t W_BYTES = W_TMEM ? 0u : 128u * (uint32_t)H * 2u, HBUF_BYTES = (uint32_t)NB * (uint32_t)H * 2u;
+  const uint32_t W_BYTES = W_TMEM ? 0u : 128u * (uint32_t)H * 2u, HBUF_BYTES = (uint32_t)MN * (uint32_t)H * 2u;
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base, sH0 = sW + W_BYTES;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));            // generic pointer to the aligned base
@@ -148,17 +156,18 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
   }
   // initial h^T buffer (step 0 input): zeros or h0 in the canonical layout
   if (warp < 4) {
-    for (int idx = threadIdx.x; idx < NB * H / 8; idx += 128) {           // one 16-byte chunk (8 k-elements) per iteration
-      const int kblk = idx / NB, b = idx % NB;
+    for (int idx = threadIdx.x; idx < MN * H / 8; idx += 128) {           // one 16-byte chunk (8 k-elements) per iteration
+      const int kblk = idx / MN, b = idx % MN;
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (p.h0 && b0 + b < p.B) {
+      *reinterpret_cast<uint4*>(gH0 + HBUF_BYTES + (size_t)(kblk * (MN / 8) + b / 8) * 128 + (b % 8) * 16) = v;   // idle columns stay 0
+      if (p.h0 && b < NB && b0 + b < p.B) {
         const float* src = p.h0 + (long long)(b0 + b) * H + kblk * 8;
         __nv_bfloat162 t0 = __floats2bfloat162_rn(src[0], src[1]), t1 = __floats2bfloat162_rn(src[2], src[3]);
         __nv_bfloat162 t2 = __floats2bfloat162_rn(src[4], src[5]), t3 = __floats2bfloat162_rn(src[6], src[7]);
         v.x = *reinterpret_cast<uint32_t*>(&t0); v.y = *reinterpret_cast<uint32_t*>(&t1);
         v.z = *reinterpret_cast<uint32_t*>(&t2); v.w = *reinterpret_cast<uint32_t*>(&t3);
       }
-      *reinterpret_cast<uint4*>(gH0 + (size_t)(kblk * (NB / 8) + b / 8) * 128 + (b % 8) * 16) = v;
+      *reinterpret_cast<uint4*>(gH0 + (size_t)(kblk * (MN / 8) + b / 8) * 128 + (b % 8) * 16) = v;
     }
     ptx::fence_proxy_async();                                             // generic writes -> visible to the MMA (async proxy)
   }
@@ -199,13 +208,13 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
         ok = ptx::mbar_wait(ptx::smem_u32(&w_full), 0);
         if (!ok) atomicExch(&g_sm100_error, 11);
       }
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NB, 0, 0);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, MN, 0, 0);
       uint32_t ph[2] = {0, 0};
       const bool have_h0 = p.h0 != nullptr;
       const uint64_t db_base[2] = {ptx::make_smem_desc(sH0, LBO_H, 128, 0), ptx::make_smem_desc(sH0 + HBUF_BYTES, LBO_H, 128, 0)};
       for (int t = 0; t < T && ok; ++t) {
         const int pb = t & 1;
-        if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[pb ^ 1]), (uint32_t)CS * SLICE_BYTES);   // h_t lands here
+        if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[pb ^ 1]), (uint32_t)CS * XCHG_BYTES);   // h_t lands here
         if (t > 0) {
           ok = ptx::mbar_wait(ptx::smem_u32(&h_full[pb]), ph[pb]);
           ph[pb] ^= 1;
@@ -272,21 +281,23 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       }
     };
     load_pre(0, pre_cur);
-    // st.async targets: this lane serves h chunk (m = octet of units, colL = column within the warp's four) to 8 peers
-    const int chunk = lane & 15, colL = chunk >> 2, m = chunk & 3;
+    // st.async targets: this lane serves h chunk (m = octet of units, colL = column within the warp's CPT) to PPL peers
+    const int chunk = lane & (NCH - 1), colL = chunk >> 2, m = chunk & 3;
     const int bcol = q * CPT + colL;
-    const uint32_t chunk_off = c * SLICE_BYTES + (uint32_t)((m * (NB / 8) + bcol / 8) * 128 + (bcol % 8) * 16);
-    const int peer0 = (lane >> 4) * 8;
-    uint32_t peer_h[8], peer_bar[8];
+    const uint32_t chunk_off = c * SLICE_BYTES + (uint32_t)((m * (MN / 8) + bcol / 8) * 128 + (bcol % 8) * 16);
+    const int peer0 = (lane / NCH) * PPL;
+    uint32_t peer_h[PPL], peer_bar[PPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < PPL; ++i) {
       const uint32_t peer = (uint32_t)min(peer0 + i, CS - 1);
       peer_h[i] = ptx::mapa(sH0, peer) + chunk_off;
       peer_bar[i] = ptx::mapa(ptx::smem_u32(&h_full[0]), peer);
     }
     const uint32_t bar_stride = ptx::smem_u32(&h_full[1]) - ptx::smem_u32(&h_full[0]);
     uint8_t* myPk = sPk + warp * 256;
-    const long long stash_blk = ((long long)nbt * CS);                    // blocks per timestep
+    // the stash keeps the 16-column block geometry of the BPTT kernel; a wide cluster fills half a block
+    const long long stash_blk = (long long)((p.B + LSTM_NB - 1) / LSTM_NB) * CS;      // blocks per timestep
+    const int bt16 = (bt * NB) / LSTM_NB, colbase = (bt * NB) % LSTM_NB;
     const bool have_h0 = p.h0 != nullptr;
     bool ok = true;
     for (int t = 0; t < T; ++t) {
@@ -300,11 +311,12 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       float x[NB];
       if (t > 0 || have_h0) {
         ptx::tc_fence_after();
-        uint32_t r[16];
-        ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
+        uint32_t r[NB];
+        if constexpr (NB == 16) ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
+        else ptx::tmem_ld_32x8(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
         ptx::tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(r[j]) + pre_cur[j];
+        for (int j = 0; j < NB; ++j) x[j] = __uint_as_float(r[j]) + pre_cur[j];
         ptx::tc_fence_before();
       } else {
 #pragma unroll
@@ -339,24 +351,24 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       if (t + 1 < T) {
         const uint32_t boff = (uint32_t)((t + 1) & 1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < PPL; ++i)
           if (peer0 + i < CS) ptx::st_async_16(peer_h[i] + boff * HBUF_BYTES, hchunk, peer_bar[i] + boff * bar_stride);
       }
       if (threadIdx.x == 0) S2VT_TRACE(6);
       // ---- off the critical path: h_t, c_t and the gate activations to HBM
-      if (lane < 16 && b0 + bcol < p.B)
+      if (lane < NCH && b0 + bcol < p.B)
         *reinterpret_cast<uint4*>(p.out + ((long long)t * p.B + b0 + bcol) * H + 32 * (int)c + 8 * m) = hchunk;
-      const long long blk = (long long)t * stash_blk + (long long)bt * CS + c;
+      const long long blk = (long long)t * stash_blk + (long long)bt16 * CS + c;
       if (p.cells) {
-        float* cdst = p.cells + blk * (NB * 32) + u;
+        float* cdst = p.cells + blk * (LSTM_NB * 32) + colbase * 32 + u;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) cdst[(q * CPT + j) * 32] = creg[j];
       }
       if (p.gates) {
         const uint4* ssrc = reinterpret_cast<const uint4*>(sStb);
-        uint4* gdst = reinterpret_cast<uint4*>(p.gates + blk * (NB * 32 * 4));
-        gdst[threadIdx.x] = ssrc[threadIdx.x];
-        gdst[threadIdx.x + 128] = ssrc[threadIdx.x + 128];
+        uint4* gdst = reinterpret_cast<uint4*>(p.gates + blk * (LSTM_NB * 32 * 4) + colbase * 32 * 4);
+#pragma unroll
+        for (int r = 0; r < NB / 8; ++r) gdst[threadIdx.x + 128 * r] = ssrc[threadIdx.x + 128 * r];
       }
       if (t == T - 1) {
 #pragma unroll
@@ -382,7 +394,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
 template <int NB, bool W_TMEM>
 static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFwdParams& p) {
   const int H = p.H, CS = H / 32;
-  const size_t smem_need = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + 2 * (size_t)NB * H * 2 + 2 * (size_t)4 * NB * 32 * 4 +
+  const size_t smem_need = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + 2 * (size_t)LSTM_MN * H * 2 + 2 * (size_t)4 * NB * 32 * 4 +
                       2 * (size_t)NB * 32 * 4 * 2 + 4 * 256;
   // This CTA owns all of the SM's tensor memory (512 columns for H = 512): a co-resident GEMM CTA from another stream would block
   // in tcgen05.alloc until the sweep ends and would contend for the SM meanwhile.  Asking for > (227 - 97) KB keeps them out.
@@ -401,7 +413,9 @@ static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFw
   cfg.attrs = attr; cfg.numAttrs = 1;
   int max_clusters = 0;
   S2VT_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  g_last_max_clusters[NB == 8 ? 0 : 1] = max_clusters;
   S2VT_REQUIRE(max_clusters >= 1, "s2vt_lstm_fwd_bf16: a cluster of %d CTAs with %zu B of shared memory cannot be scheduled on this device", CS, smem);
+  if (NB < LSTM_NB && max_clusters < ceil_div(p.B, NB)) return -1;       // the wide form must be fully co-resident; caller falls back
   S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, p));
   count_launch();
   return 0;
@@ -441,10 +455,16 @@ extern "C" int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
     return launch_lstm_fwd<LSTM_NB, false>((cudaStream_t)stream, tmW, p);
   }
   memset(&tmW, 0, sizeof(tmW));
+  // wide form (8 columns per cluster): half the DSMEM exchange and epilogue work per step, when all ceil(B/8) clusters fit at once
+  if (!(g_dbg_flags & 32) && B > 8 && ceil_div(B, 8) * (H / 32) <= 128) {
+    const int rc = launch_lstm_fwd<8, true>((cudaStream_t)stream, tmW, p);
+    if (rc >= 0) return rc;
+  }
   return launch_lstm_fwd<LSTM_NB, true>((cudaStream_t)stream, tmW, p);
 }
 
 // debug aids (not part of the product path): per-step clock64 stamps of CTA 0 for steps [16, 48)
+extern "C" int s2vt_debug_max_clusters(int which) { return g_last_max_clusters[which & 1]; }
 extern "C" int s2vt_debug_trace_enable(int on) { g_trace_enabled = on != 0; return 0; }
 extern "C" int s2vt_debug_set_flags(int flags) { g_dbg_flags = flags; return 0; }
 extern "C" int s2vt_debug_trace_read(long long* host_out, int n) {

@@ -179,12 +179,67 @@ extern "C" int s2vt_embed_gather_bf16(void* stream, const void* table_bf16, int 
   return 0;
 }
 
+namespace s2vt {
+// Wide form: a thread owns 8 adjacent columns (one 16-byte load per row, four rows in flight), a warp 256 columns, the 8 warps of a
+// block split the rows.  grid = (ceil(N/256), row chunks); partial sums meet in shared memory, one atomicAdd per column and block.
+__global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const __nv_bfloat16* __restrict__ X, long long M, int N, long long ld,
+                                                             float* __restrict__ out, float* __restrict__ out2) {
+  __shared__ float sh[8][257];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 256 + lane * 8;
+  const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const long long m0 = (long long)blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  auto acc = [&](const uint4& v) {
+    a[0] += __uint_as_float(v.x << 16); a[1] += __uint_as_float(v.x & 0xffff0000u);
+    a[2] += __uint_as_float(v.y << 16); a[3] += __uint_as_float(v.y & 0xffff0000u);
+    a[4] += __uint_as_float(v.z << 16); a[5] += __uint_as_float(v.z & 0xffff0000u);
+    a[6] += __uint_as_float(v.w << 16); a[7] += __uint_as_float(v.w & 0xffff0000u);
+  };
+  if (n < N) {
+    const __nv_bfloat16* src = X + n;
+    long long m = m0 + warp;
+    for (; m + 24 < m1; m += 32) {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src + m * ld));
+      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(src + (m + 8) * ld));
+      const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(src + (m + 16) * ld));
+      const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(src + (m + 24) * ld));
+      acc(v0); acc(v1); acc(v2); acc(v3);
+    }
+    for (; m < m1; m += 8) acc(__ldg(reinterpret_cast<const uint4*>(src + m * ld)));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[warp][lane * 8 + j] = a[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    atomicAdd(out + col, t);
+    if (out2) atomicAdd(out2 + col, t);
+  }
+}
+}  // namespace s2vt
+
 extern "C" int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t ld, float* out, float* out2) {
   S2VT_REQUIRE(X_bf16 && out, "s2vt_colsum_bf16: null pointer");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   S2VT_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
   if (out2) S2VT_CHECK_CUDA(cudaMemsetAsync(out2, 0, sizeof(float) * N, st));
+  if (N % 8 == 0 && ld % 8 == 0 && aligned16(X_bf16)) {
+    const int gx8 = ceil_div(N, 256);
+    int gy8 = ceil_div(148 * 4, gx8);                   // ~4 blocks of 256 threads per SM in total
+    const int max_gy8 = ceil_div(M, 32);
+    if (gy8 > max_gy8) gy8 = max_gy8;
+    if (gy8 < 1) gy8 = 1;
+    colsum_bf16_v8_kernel<<<dim3(gx8, gy8), 256, 0, st>>>((const __nv_bfloat16*)X_bf16, M, N, ld, out, out2);
+    S2VT_CHECK_LAUNCH();
+    return 0;
+  }
   const int gx = ceil_div(N, 64);
   int gy = ceil_div(148 * 8, gx);                       // ~8 CTAs per SM in total
   const int max_gy = ceil_div(M, 64);

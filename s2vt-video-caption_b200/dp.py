@@ -31,7 +31,7 @@ def bucket_ranges(names: Sequence[str], offsets: Sequence[int], sizes: Sequence[
     for bname, members in BUCKETS:
         spans = sorted(pos[m] for m in members)
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
-            if b0 - a1 > 3:                      # 16-byte alignment padding only
+            if b0 - a1 > 7:                      # alignment padding only
                 raise ValueError("bucket %s is not contiguous in the flat buffer" % bname)
         out[bname] = (spans[0][0], spans[-1][1])
     return out

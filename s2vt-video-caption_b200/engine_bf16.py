@@ -42,8 +42,8 @@ def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None
     L.check(rc, "s2vt_gemm_bf16")
 
 
-def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False):
-    dst = torch.empty(rows, cols, dtype=BF, device=src.device)
+def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False, want_plain: bool = True):
+    dst = torch.empty(rows, cols, dtype=BF, device=src.device) if want_plain else None
     dst_t = torch.empty(cols, rows, dtype=BF, device=src.device) if want_t else None
     with ops._timed("cast_bf16", 0.0, 6.0 * rows * cols):
         rc = L.load().s2vt_cast_bf16(L.stream_ptr(src.device), L.ptr(src), L.ptr(dst), L.ptr(dst_t), rows, cols)
@@ -88,17 +88,22 @@ class ShadowCache:
         self.key = None
         self.t: Dict[str, torch.Tensor] = {}
 
-    def get(self, P: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    def get(self, P: Dict[str, torch.Tensor], adam=None) -> Dict[str, torch.Tensor]:
+        """`adam`: the attached FusedAdam, whose kernel already wrote a bf16 copy of every weight it updated."""
         key = (ops.WEIGHT_EPOCH,) + tuple((p.data_ptr(), p._version) for p in P.values())
         if key == self.key:
             return self.t
+        fused = adam.shadow_views(list(P.items())) if adam is not None else None
         t = {}
         for name in ("feat_linear.weight", "vid_rnn.weight_ih_l0", "word_rnn.weight_ih_l0", "out_linear.weight", "embedding.weight"):
             w = P[name]
-            t[name], _ = cast(w, w.shape[0], w.shape[1])
+            t[name] = fused[name] if fused is not None else cast(w, w.shape[0], w.shape[1])[0]
         for name in ("vid_rnn.weight_hh_l0", "word_rnn.weight_hh_l0"):
             w = P[name]
-            t[name], t[name + ".T"] = cast(w, w.shape[0], w.shape[1], want_t=True)
+            if fused is not None:
+                t[name], t[name + ".T"] = fused[name], cast(w, w.shape[0], w.shape[1], want_t=True, want_plain=False)[1]
+            else:
+                t[name], t[name + ".T"] = cast(w, w.shape[0], w.shape[1], want_t=True)
         t["b1"] = ops.add_f32(P["vid_rnn.bias_ih_l0"], P["vid_rnn.bias_hh_l0"], torch.empty_like(P["vid_rnn.bias_ih_l0"]))
         t["b2"] = ops.add_f32(P["word_rnn.bias_ih_l0"], P["word_rnn.bias_hh_l0"], torch.empty_like(P["word_rnn.bias_ih_l0"]))
         self.key, self.t = key, t

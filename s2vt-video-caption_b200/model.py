@@ -303,7 +303,7 @@ class _TrainLossFn(torch.autograd.Function):
         loss = torch.empty((), device=feats.device)
         # row (t,b) of the time-major logits is scored against targets_full[b, t+1]
         if ctx.bf16:
-            ctx.S = module._shadow.get(P)
+            ctx.S = module._shadow.get(P, getattr(module, '_adam_shadow', None))
             logits, saved = EB.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False)
             ctx.lse = torch.empty((L - 1) * B, device=feats.device)
             EB.ce_bf16(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss=loss, row_lse=ctx.lse)
@@ -342,7 +342,7 @@ class _TrainLogitsBf16Fn(torch.autograd.Function):
     def forward(ctx, module, feats, targets, *params):
         P = dict(zip(PARAM_ORDER, params))
         need = any(ctx.needs_input_grad)
-        ctx.S = module._shadow.get(P)
+        ctx.S = module._shadow.get(P, getattr(module, '_adam_shadow', None))
         logits, saved = EB.train_forward(P, ctx.S, feats, targets, stash=need, batch_major_logits=True)
         ctx.saved, ctx.P, ctx.targets, ctx.module = saved, P, targets, module
         return logits
@@ -389,11 +389,12 @@ class S2VT(nn.Module):
         self.beam_topk = 20                     # S2VTModel.py:216
         self._grad_views = None                 # set by FusedAdam.attach(): backward writes gradients in place
         self._on_bucket_ready = None
+        self._adam_shadow = None                # set by FusedAdam.attach(): its kernel keeps bf16 copies of the weights current
         self._shadow = EB.ShadowCache()         # bf16 mirrors of the weights (derived, rebuilt lazily, never saved)
 
     def __getstate__(self):
         st = self.__dict__.copy()               # whole-module pickles (train.py:167) carry parameters only
-        st["_grad_views"], st["_on_bucket_ready"], st["_shadow"] = None, None, EB.ShadowCache()
+        st["_grad_views"], st["_on_bucket_ready"], st["_adam_shadow"], st["_shadow"] = None, None, None, EB.ShadowCache()
         return st
 
     def _use_bf16(self) -> bool:

@@ -32,7 +32,7 @@ class FusedAdam(torch.optim.Optimizer):
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("FusedAdam needs float32 parameters on one device")
             offsets.append(n)
-            n += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+            n += (p.numel() + 7) // 8 * 8          # keep every tensor 16-byte aligned, in fp32 and in the bf16 shadow
         flat = torch.zeros(n, device=dev)
         old = self._flat
         for p, o in zip(ps, offsets):
@@ -45,7 +45,9 @@ class FusedAdam(torch.optim.Optimizer):
         step = 0
         if old is not None and old["p"].numel() == n:
             m.copy_(old["m"]); v2.copy_(old["v"]); step = old["step"]
-        self._flat = dict(params=ps, offsets=offsets, p=flat, g=g, m=m, v=v2, step=step, n=n)
+        # bf16 shadow of the weights, refreshed by the Adam kernel itself (the tensor-core path reads weights as bf16)
+        shadow = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        self._flat = dict(params=ps, offsets=offsets, p=flat, g=g, m=m, v=v2, step=step, n=n, shadow=shadow, shadow_state=None)
         return self._flat
 
     def flat_grad_views(self):
@@ -62,6 +64,22 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("attach(): the optimizer must have been built from model.parameters()")
         model._grad_views = dict(zip(names, views))
         model._on_bucket_ready = on_bucket_ready
+        model._adam_shadow = self            # engine_bf16.ShadowCache asks shadow_views() for weights the last step() already cast
+
+    def shadow_views(self, named_params):
+        """{name: bf16 view} of the weights as written by the last Adam kernel, or None when they are stale (no step yet, another
+        optimizer stepped since, or a parameter was modified in place / re-homed since)."""
+        f = self._flat
+        if f is None or f["shadow_state"] is None:
+            return None
+        epoch, versions = f["shadow_state"]
+        params = [p for _, p in named_params]
+        if epoch != ops.WEIGHT_EPOCH or len(params) != len(f["params"]) or any(a is not b for a, b in zip(params, f["params"])):
+            return None
+        base = f["p"].data_ptr()
+        if versions != tuple(p._version for p in params) or any(p.data_ptr() != base + o * 4 for p, o in zip(params, f["offsets"])):
+            return None
+        return {n: f["shadow"][o:o + p.numel()].view(p.shape) for (n, p), o in zip(named_params, f["offsets"])}
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -79,5 +97,6 @@ class FusedAdam(torch.optim.Optimizer):
         group = self.param_groups[0]
         f["step"] += 1
         ops.adam_f32(f["p"], f["g"], f["m"], f["v"], float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
-                     float(group["eps"]), f["step"], grad_scale=grad_scale)
+                     float(group["eps"]), f["step"], grad_scale=grad_scale, bf16_copy=f["shadow"])
+        f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))
         return loss
