@@ -212,6 +212,22 @@ int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t
 int s2vt_ce_bf16(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
                  float* row_loss, float* loss, float* row_lse, int have_lse, void* dlogits_bf16, const float* gscale);
 
+/* ------------------------------------------------------------------ vocab projection fused with the loss statistics
+ * logits = A W^T + bias on the tensor cores (A [R,K] bf16, W [V,K] bf16), written ONCE as bf16 [R, ldl]; the GEMM epilogue also
+ * reduces, from the fp32 accumulators, each row's online-softmax partials per 256-column tile and picks out the target logit, so
+ * the mean cross entropy needs no further pass over the logits:
+ *   part_ws  >= s2vt_vocab_ce_ws_bytes(R, V) bytes, ztgt_ws [R] floats: scratch
+ *   row_lse [R] out (log-sum-exp per row, kept for the backward call);  row_loss [R] scratch, loss: 1 float out (both nullable)
+ * replaces: self.out_linear(...) at S2VTModel.py:80 + nn.CrossEntropyLoss inside MaskCriterion, utils.py:11,22. */
+int64_t s2vt_vocab_ce_ws_bytes(int R, int V);
+int s2vt_vocab_ce_fwd_bf16(void* stream, int R, int V, int K, const void* A_bf16, int64_t lda, const void* W_bf16, int64_t ldw,
+                           const float* bias, void* logits_bf16, int64_t ldl, const int64_t* targets, s2vt_rowmap tmap,
+                           void* part_ws, float* ztgt_ws, float* row_lse, float* row_loss, float* loss);
+/* In place: bf16 logits -> bf16 dL/dlogits = (softmax - onehot) * gscale[0] / R, using the rows' log-sum-exp from the forward
+ * call (replaces: autograd of nn.CrossEntropyLoss under loss.backward(), train.py:124). */
+int s2vt_ce_dlogits_inplace_bf16(void* stream, void* logits_bf16, int64_t R, int V, int64_t ld, const float* row_lse,
+                                 const int64_t* targets, s2vt_rowmap tmap, const float* gscale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,9 +22,9 @@ int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
 
 int gemm_persist_error_flag() { return read_sm100_error_flag(); }
 
-constexpr int PBM = 128, PBN = 256, PBK = 64, PSTAGES = 4, PRING = 4;
+constexpr int PBM = 128, PBN = 256, PBK = 64, PSTAGES = 4, PRING = 4, PNSTG = 2;
 constexpr int PA_BYTES = PBM * PBK * 2, PB_BYTES = PBN * PBK * 2, PSTAGE_BYTES = PA_BYTES + PB_BYTES;
-constexpr int PSTG_WARP = 2 * 4096;                                   // per epilogue warp: two 32-row x 128-byte staging boxes
+constexpr int PSTG_WARP = PNSTG * 4096;                               // per epilogue warp: PNSTG 32-row x 128-byte staging boxes
 constexpr int PSMEM = PSTAGES * PSTAGE_BYTES + 4 * PSTG_WARP + 1024;
 constexpr int SCHED_SLOTS = 1024;
 __device__ unsigned int g_gemm_sched[2 * SCHED_SLOTS];                // per launch slot: {next unit, finished CTAs}; self-resetting
@@ -36,6 +36,12 @@ struct GemmPersistParams {
   int out_bf16, reduce;
   const float* bias;
   unsigned int* sched;
+  // fused cross-entropy statistics (vocab projection, bf16 output only): per (row, n-tile) online-softmax partials of the fp32
+  // logits BEFORE they are rounded to bf16, and the fp32 logit of each row's target
+  float2* ce_part;                  // [M][tiles_n] (max, sum exp(z - max)) or null
+  float* ce_ztgt;                   // [M]
+  const int64_t* ce_targets;
+  RowMap ce_tmap;
 };
 
 namespace ptx {
@@ -48,7 +54,7 @@ __device__ __forceinline__ void p_tma_reduce_add_2d(const CUtensorMap* m, uint32
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void p_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void p_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void p_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PNSTG - 1) : "memory"); }
 __device__ __forceinline__ void p_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 }  // namespace ptx
 
@@ -225,7 +231,7 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           if (lane == 0) ptx::p_bulk_wait_read1();                 // the store that used this staging box two chunks ago has read it
           __syncwarp();
-          const uint32_t box = my_row + (nstore & 1) * 4096u;
+          const uint32_t box = my_row + (nstore % PNSTG) * 4096u;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(box + (uint32_t)((j ^ (lane & 7)) * 16)),
@@ -233,8 +239,8 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0 && row0 < p.M) {
-            if (p.reduce) ptx::p_tma_reduce_add_2d(&tmC, stg + (nstore & 1) * 4096u, n, row0);
-            else ptx::p_tma_store_2d(&tmC, stg + (nstore & 1) * 4096u, n, row0);
+            if (p.reduce) ptx::p_tma_reduce_add_2d(&tmC, stg + (nstore % PNSTG) * 4096u, n, row0);
+            else ptx::p_tma_store_2d(&tmC, stg + (nstore % PNSTG) * 4096u, n, row0);
             ptx::p_bulk_commit();
           } else if (lane == 0) {
             ptx::p_bulk_commit();                                   // keep the group count in step with nstore
@@ -243,6 +249,10 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       } else {
         const int nchunk = min(PBN / 64, (p.N - n0 + 63) / 64);
+        const int my_m = row0 + lane;
+        float ce_m = -INFINITY, ce_s = 0.f;
+        long long ce_tgt = -1;
+        if (p.ce_part && my_m < p.M) ce_tgt = p.ce_targets[p.ce_tmap(my_m)];
         for (int c = 0; c < nchunk; ++c) {
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32(t_acc + (uint32_t)(c * 64), r0);
@@ -261,9 +271,35 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
           }
+          if (p.ce_part) {
+            constexpr float LOG2E = 1.4426950408889634f;
+            if (n + 64 > p.N) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) if (n + j >= p.N) v[j] = -INFINITY;
+            }
+            float cm = v[0];
+#pragma unroll
+            for (int j = 1; j < 64; ++j) cm = fmaxf(cm, v[j]);
+            const float mn = fmaxf(ce_m, cm);
+            const float off = mn * LOG2E;
+            float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              cs0 += exp2f(fmaf(v[j], LOG2E, -off));
+              cs1 += exp2f(fmaf(v[j + 1], LOG2E, -off));
+            }
+            ce_s = ce_s * exp2f((ce_m - mn) * LOG2E) + (cs0 + cs1);
+            ce_m = mn;
+            if ((unsigned long long)(ce_tgt - n) < 64ull) {          // rare: exactly one chunk per row holds the target column
+              float zt = 0.f;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) if (n + j == ce_tgt) zt = v[j];
+              p.ce_ztgt[my_m] = zt;
+            }
+          }
           if (lane == 0) ptx::p_bulk_wait_read1();
           __syncwarp();
-          const uint32_t box = my_row + (nstore & 1) * 4096u;
+          const uint32_t box = my_row + (nstore % PNSTG) * 4096u;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), t1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
@@ -275,11 +311,12 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (row0 < p.M) ptx::p_tma_store_2d(&tmC, stg + (nstore & 1) * 4096u, n, row0);
+            if (row0 < p.M) ptx::p_tma_store_2d(&tmC, stg + (nstore % PNSTG) * 4096u, n, row0);
             ptx::p_bulk_commit();
           }
           ++nstore;
         }
+        if (p.ce_part && my_m < p.M) p.ce_part[(long long)my_m * p.tiles_n + (tile % p.tiles_n)] = make_float2(ce_m, ce_s);
       }
     }
     if (lane == 0) ptx::p_bulk_wait0();                            // all stores of this warp have landed before the CTA retires
@@ -301,8 +338,9 @@ static thread_local int g_max_ctas = 0;      // 0 = all SMs
 static int g_num_sms = 0;
 
 // Returns 0 on success, < 0 when this kernel does not cover the case (caller falls back), > 0 on error.
-int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
-                        void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate) {
+int launch_gemm_persist_ce(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                           void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate,
+                           float2* ce_part, float* ce_ztgt, const int64_t* ce_targets, RowMap ce_tmap) {
   if (out_bf16 && accumulate) return -1;
   if (!g_num_sms) {
     int dev = 0;
@@ -325,6 +363,7 @@ int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int
   p.tiles_n = ceil_div(N, PBN);
   p.tiles = p.tiles_n * ceil_div(M, PBM);
   p.out_bf16 = out_bf16; p.bias = bias;
+  p.ce_part = ce_part; p.ce_ztgt = ce_ztgt; p.ce_targets = ce_targets; p.ce_tmap = ce_tmap;
   // split K so that the unit count fills whole rounds of the G resident CTAs (fp32 outputs only: partials are summed in L2 by TMA)
   int best = 1;
   if (!out_bf16) {
@@ -365,6 +404,125 @@ int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int
   return 0;
 }
 
+int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
+                        void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate) {
+  return launch_gemm_persist_ce(st, M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, out_bf16, bias, accumulate, nullptr, nullptr, nullptr, RowMap{1, 1, 0});
+}
+
 void gemm_persist_set_max_ctas(int n) { g_max_ctas = n; }
 
+// one warp per row: merge the per-tile (max, sum-exp) partials -> log-sum-exp; row loss = lse - z[target]
+__global__ void ce_combine_kernel(const float2* __restrict__ part, int tiles_n, const float* __restrict__ ztgt, long long R,
+                                  float* __restrict__ row_lse, float* __restrict__ row_loss) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  float m = -INFINITY, s = 0.f;
+  for (int j = lane; j < tiles_n; j += 32) {
+    const float2 v = part[r * tiles_n + j];
+    const float mn = fmaxf(m, v.x);
+    s = s * __expf(m - mn) + v.y * __expf(v.x - mn);
+    m = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, m2);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+    m = mn;
+  }
+  if (lane == 0) {
+    const float lse = m + logf(s);
+    row_lse[r] = lse;
+    if (row_loss) row_loss[r] = lse - ztgt[r];
+  }
+}
+
+__global__ void ce_mean_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float a = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) a += x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float b = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (threadIdx.x == 0) out[0] = b / (float)n;
+  }
+}
+
+// in place: z (bf16 logits) -> (softmax - onehot) * gscale / R as bf16; one block per row, 16-byte accesses
+__global__ void __launch_bounds__(256) ce_dlogits_inplace_kernel(__nv_bfloat16* __restrict__ z, int V, long long ld, const float* __restrict__ row_lse,
+                                                                 const int64_t* __restrict__ targets, RowMap tmap, const float* __restrict__ gscale,
+                                                                 float inv_rows) {
+  const long long r = blockIdx.x;
+  __nv_bfloat16* row = z + r * ld;
+  const float lse = row_lse[r];
+  const long long tgt = targets[tmap(r)];
+  const float sc = (gscale ? gscale[0] : 1.f) * inv_rows;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float off = lse * LOG2E;
+  const int nv = V / 8;
+  uint4* row4 = reinterpret_cast<uint4*>(row);
+  for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+    uint4 v = row4[j];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const long long j0 = 8ll * j;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = exp2f(fmaf(__uint_as_float(w[k] << 16), LOG2E, -off));
+      float b = exp2f(fmaf(__uint_as_float(w[k] & 0xffff0000u), LOG2E, -off));
+      if (j0 + 2 * k == tgt) a -= 1.f;
+      if (j0 + 2 * k + 1 == tgt) b -= 1.f;
+      const __nv_bfloat162 t2 = __floats2bfloat162_rn(a * sc, b * sc);
+      w[k] = *reinterpret_cast<const uint32_t*>(&t2);
+    }
+    row4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int j = nv * 8 + threadIdx.x; j < V; j += blockDim.x) {
+    float a = exp2f(fmaf(__bfloat162float(row[j]), LOG2E, -off));
+    if (j == tgt) a -= 1.f;
+    row[j] = __float2bfloat16(a * sc);
+  }
+}
+
 }  // namespace s2vt
+
+using namespace s2vt;
+
+extern "C" int s2vt_vocab_ce_fwd_bf16(void* stream, int R, int V, int K, const void* A_bf16, int64_t lda, const void* W_bf16, int64_t ldw,
+                                      const float* bias, void* logits_bf16, int64_t ldl, const int64_t* targets, s2vt_rowmap tmap,
+                                      void* part_ws, float* ztgt_ws, float* row_lse, float* row_loss, float* loss) {
+  S2VT_REQUIRE(R > 0 && V > 0 && K > 0, "s2vt_vocab_ce_fwd_bf16: bad dims");
+  S2VT_REQUIRE(A_bf16 && W_bf16 && logits_bf16 && targets && part_ws && ztgt_ws && row_lse, "s2vt_vocab_ce_fwd_bf16: null pointer");
+  S2VT_REQUIRE(!loss || row_loss, "s2vt_vocab_ce_fwd_bf16: loss needs row_loss scratch");
+  S2VT_REQUIRE(aligned16(logits_bf16) && ldl % 8 == 0 && ldl >= V, "s2vt_vocab_ce_fwd_bf16: logits must be 16-byte aligned with ld %% 8 == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_gemm_persist_ce(st, R, V, K, A_bf16, lda, 0, W_bf16, ldw, 0, logits_bf16, ldl, 1, bias, 0, (float2*)part_ws, ztgt_ws, targets,
+                                  to_rowmap(tmap));
+  if (rc) return rc < 0 ? fail("s2vt_vocab_ce_fwd_bf16: unsupported configuration") : rc;
+  const int tiles_n = ceil_div(V, PBN);
+  ce_combine_kernel<<<ceil_div(R, 8), 256, 0, st>>>((const float2*)part_ws, tiles_n, ztgt_ws, R, row_lse, row_loss);
+  S2VT_CHECK_LAUNCH();
+  if (loss) {
+    ce_mean_kernel<<<1, 1024, 0, st>>>(row_loss, R, loss);
+    S2VT_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int64_t s2vt_vocab_ce_ws_bytes(int R, int V) { return (int64_t)R * ceil_div(V, PBN) * (int64_t)sizeof(float2); }
+
+extern "C" int s2vt_ce_dlogits_inplace_bf16(void* stream, void* logits_bf16, int64_t R, int V, int64_t ld, const float* row_lse,
+                                            const int64_t* targets, s2vt_rowmap tmap, const float* gscale) {
+  S2VT_REQUIRE(logits_bf16 && row_lse && targets, "s2vt_ce_dlogits_inplace_bf16: null pointer");
+  S2VT_REQUIRE(aligned16(logits_bf16) && ld % 8 == 0, "s2vt_ce_dlogits_inplace_bf16: logits must be 16-byte aligned with ld %% 8 == 0");
+  if (R == 0) return 0;
+  ce_dlogits_inplace_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)logits_bf16, V, ld, row_lse, targets, to_rowmap(tmap), gscale,
+                                                                          1.0f / (float)R);
+  S2VT_CHECK_LAUNCH();
+  return 0;
+}

@@ -123,8 +123,34 @@ def _chain_stream(dev) -> torch.cuda.Stream:
 
 
 # ------------------------------------------------------------------------------------------------ forward / backward
-def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool):
-    """S2VT.forward(mode='train') on tensor cores (S2VTModel.py:48-81).  Returns (fp32 logits, saved)."""
+def vocab_ce_fwd(R, V, K, A, a_off, W, bias, targets_full, t_off, tmap, loss):
+    """out_linear fused with the loss statistics: returns (bf16 logits [R,V], row log-sum-exp [R]); `loss` receives the mean CE."""
+    lib = L.load()
+    dev = A.device
+    logits = torch.empty(R, V, dtype=BF, device=dev)
+    part = torch.empty(int(lib.s2vt_vocab_ce_ws_bytes(R, V)), dtype=torch.uint8, device=dev)
+    ztgt = torch.empty(R, device=dev)
+    lse = torch.empty(R, device=dev)
+    row_loss = torch.empty(R, device=dev)
+    with ops._timed("gemm_bf16[%dx%dx%d NN bf16out +CE]" % (R, V, K), 2.0 * R * V * K, 2.0 * (R * K + V * K) + 2.0 * R * V):
+        rc = lib.s2vt_vocab_ce_fwd_bf16(L.stream_ptr(dev), R, V, K, L.ptr(A, a_off), K, L.ptr(W), K, L.ptr(bias), L.ptr(logits), V,
+                                        L.ptr(targets_full, t_off), tmap, L.ptr(part), L.ptr(ztgt), L.ptr(lse), L.ptr(row_loss), L.ptr(loss))
+    L.check(rc, "s2vt_vocab_ce_fwd_bf16")
+    return logits, lse
+
+
+def ce_dlogits_inplace(logits_bf, R, V, lse, targets_full, t_off, tmap, gscale):
+    with ops._timed("ce_bf16", 0.0, 4.0 * R * V):
+        rc = L.load().s2vt_ce_dlogits_inplace_bf16(L.stream_ptr(logits_bf.device), L.ptr(logits_bf), R, V, V, L.ptr(lse), L.ptr(targets_full, t_off),
+                                                   tmap, L.ptr(gscale))
+    L.check(rc, "s2vt_ce_dlogits_inplace_bf16")
+    return logits_bf
+
+
+def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, ce=None):
+    """S2VT.forward(mode='train') on tensor cores (S2VTModel.py:48-81).  Returns (fp32 logits, saved); with ce = dict(targets_full,
+    t_off, tmap, loss) the vocab projection is fused with the loss and (bf16 time-major logits, saved) is returned, saved['lse']
+    holding the rows' log-sum-exp."""
     B, Lq, F = feats.shape
     H = P["vid_rnn.weight_hh_l0"].shape[1]
     V, E = P["embedding.weight"].shape
@@ -154,14 +180,19 @@ def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool):
     c2 = torch.empty(T * Bp * H, device=dev) if stash else None
     lstm_fwd(T, B, H, T, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2)
     R = (Lq - 1) * B
-    if batch_major_logits:
-        logits = torch.empty(B, Lq - 1, V, device=dev)
-        cmap = rowmap(B, V, (Lq - 1) * V)
+    lse = None
+    if ce is not None:
+        logits, lse = vocab_ce_fwd(R, V, H, out2, Lq * B * H, S["out_linear.weight"], P["out_linear.bias"], ce["targets_full"], ce["t_off"],
+                                   ce["tmap"], ce["loss"])
     else:
-        logits = torch.empty(R, V, device=dev)
-        cmap = dense(V)
-    gemm(R, V, H, out2, H, False, S["out_linear.weight"], H, False, logits, cmap, bias=P["out_linear.bias"], a_off=Lq * B * H)
-    saved = dict(xb=xb, xproj=xproj, out1=out1, g1=g1, c1=c1, out2=out2, g2=g2, c2=c2, emb_seq=emb_seq,
+        if batch_major_logits:
+            logits = torch.empty(B, Lq - 1, V, device=dev)
+            cmap = rowmap(B, V, (Lq - 1) * V)
+        else:
+            logits = torch.empty(R, V, device=dev)
+            cmap = dense(V)
+        gemm(R, V, H, out2, H, False, S["out_linear.weight"], H, False, logits, cmap, bias=P["out_linear.bias"], a_off=Lq * B * H)
+    saved = dict(xb=xb, xproj=xproj, out1=out1, g1=g1, c1=c1, out2=out2, g2=g2, c2=c2, emb_seq=emb_seq, lse=lse,
                  dims=(B, Lq, F, H, E, V, T)) if stash else None
     return logits, saved
 

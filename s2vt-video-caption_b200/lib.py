@@ -52,6 +52,9 @@ SIGNATURES = {
     "s2vt_colsum_bf16": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp]),
     "s2vt_ce_bf16": (_i, [_vp, _vp, _i64, _i, _vp, RowMap, _vp, _vp, _vp, _i, _vp, _vp]),
     "s2vt_bcast_rows_f32": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    "s2vt_vocab_ce_ws_bytes": (_i64, [_i, _i]),
+    "s2vt_vocab_ce_fwd_bf16": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, RowMap, _vp, _vp, _vp, _vp, _vp]),
+    "s2vt_ce_dlogits_inplace_bf16": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp, RowMap, _vp]),
     "s2vt_add_f32": (_i, [_vp, _vp, _vp, _vp, _i64]),
     "s2vt_colsum_f32": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _i]),
     "s2vt_ce_f32": (_i, [_vp, _vp, _i64, _i, _vp, RowMap, _vp, _vp, _vp, _vp]),

@@ -304,9 +304,9 @@ class _TrainLossFn(torch.autograd.Function):
         # row (t,b) of the time-major logits is scored against targets_full[b, t+1]
         if ctx.bf16:
             ctx.S = module._shadow.get(P, getattr(module, '_adam_shadow', None))
-            logits, saved = EB.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False)
-            ctx.lse = torch.empty((L - 1) * B, device=feats.device)
-            EB.ce_bf16(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss=loss, row_lse=ctx.lse)
+            # vocab projection + loss statistics in one kernel: the logits are written once, as bf16
+            logits, saved = EB.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False,
+                                             ce=dict(targets_full=targets_full, t_off=1, tmap=rowmap(B, 1, L), loss=loss))
         else:
             logits, saved = train_forward_f32(P, feats, tin, stash=need, batch_major_logits=False)
             ops.ce_f32(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss)
@@ -321,8 +321,7 @@ class _TrainLossFn(torch.autograd.Function):
         g = gloss.contiguous().to(torch.float32)
         direct, cb = _direct_grad_targets(ctx.module)
         if ctx.bf16:
-            dl = torch.empty((L - 1) * B, V, dtype=torch.bfloat16, device=logits.device)
-            EB.ce_bf16(logits, (L - 1) * B, V, ctx.tfull, 1, rowmap(B, 1, L), dlogits=dl, gscale=g, row_lse=ctx.lse, have_lse=True)
+            dl = EB.ce_dlogits_inplace(logits, (L - 1) * B, V, ctx.saved["lse"], ctx.tfull, 1, rowmap(B, 1, L), g)
             G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
             grads, dfeats = [G[k] for k in PARAM_ORDER], G.get("feats")
         else:

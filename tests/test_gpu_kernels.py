@@ -193,3 +193,45 @@ def test_cast_bf16(dev):
     d2 = torch.empty(70 * 130, dtype=torch.bfloat16, device=dev)
     L.check(L.load().s2vt_cast_bf16(L.stream_ptr(dev), L.ptr(x), L.ptr(d2), None, 70, 130), "cast")
     assert torch.equal(d2.view(70, 130), x.bfloat16())
+
+
+@pytest.mark.parametrize("R,V,K", [(300, 1000, 128), (5056, 13000, 512), (129, 520, 64)])
+def test_vocab_projection_fused_with_ce(dev, R, V, K):
+    """s2vt_vocab_ce_fwd_bf16 / s2vt_ce_dlogits_inplace_bf16 against a plain fp32 torch reference of the same op
+    (bf16 operands, fp32 accumulation): loss rtol 1e-4, lse atol 1e-4, logits to bf16 resolution, dlogits to bf16 resolution."""
+    from s2vt_b200.lib import rowmap
+    g = torch.Generator().manual_seed(R + V)
+    lib = L.load()
+    A = (torch.randn(R, K, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(V, K, generator=g) * (2.0 / K ** 0.5)).to(dev).bfloat16()
+    bias = torch.randn(V, generator=g).to(dev)
+    Bq, Lq = 4, R // 4 + 1                                   # targets addressed through a row map, like targets_full[b, t+1]
+    tg_full = torch.randint(0, V, (Bq, Lq + 1), generator=g).to(dev)
+    tmap = rowmap(Bq, 1, Lq + 1)                             # row r -> tg_full[r % Bq, r // Bq + 1]
+    rows = torch.arange(R, device=dev)
+    tgt = tg_full[rows % Bq, rows // Bq + 1]
+    z = A.float() @ W.float().T + bias
+    lse_ref = torch.logsumexp(z.double(), dim=1)
+    loss_ref = (lse_ref - z.double()[rows, tgt]).mean().item()
+    logits = torch.empty(R, V, device=dev, dtype=torch.bfloat16)
+    part = torch.empty(int(lib.s2vt_vocab_ce_ws_bytes(R, V)), dtype=torch.uint8, device=dev)
+    ztgt, lse, row_loss = (torch.empty(R, device=dev) for _ in range(3))
+    loss = torch.empty((), device=dev)
+    rc = lib.s2vt_vocab_ce_fwd_bf16(L.stream_ptr(dev), R, V, K, L.ptr(A), K, L.ptr(W), K, L.ptr(bias), L.ptr(logits), V, L.ptr(tg_full, 1), tmap,
+                                    L.ptr(part), L.ptr(ztgt), L.ptr(lse), L.ptr(row_loss), L.ptr(loss))
+    L.check(rc, "s2vt_vocab_ce_fwd_bf16")
+    assert lib.s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+    assert abs(loss.item() - loss_ref) <= 1e-4 * abs(loss_ref)
+    assert (lse.double() - lse_ref).abs().max().item() <= 1e-4 * max(1.0, lse_ref.abs().max().item())
+    assert (logits.float() - z).abs().max().item() <= 2 ** -8 * z.abs().max().item() + 1e-6
+    gs = torch.tensor(0.7, device=dev)
+    rc = lib.s2vt_ce_dlogits_inplace_bf16(L.stream_ptr(dev), L.ptr(logits), R, V, V, L.ptr(lse), L.ptr(tg_full, 1), tmap, L.ptr(gs))
+    L.check(rc, "s2vt_ce_dlogits_inplace_bf16")
+    prob = torch.softmax(z.double(), dim=1)
+    dref = prob.clone()
+    dref[rows, tgt] -= 1.0
+    dref *= 0.7 / R
+    err = (logits.double() - dref).abs()
+    # the probabilities come from bf16-rounded logits (relative error <= |z| * 2^-9 each), the result is rounded to bf16 (2^-9)
+    tol = 2 ** -8 * (1.0 + z.double().abs()) * prob * (0.7 / R) + 2 ** -8 * dref.abs() + 1e-12
+    assert (err <= tol).all(), (err - tol).max().item()
