@@ -196,15 +196,25 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int split = unit / p.tiles, tile = unit % p.tiles;
       const int n0 = (tile % p.tiles_n) * PBN, m0 = (tile / p.tiles_n) * PBM;
       const uint32_t a = ai & 1;
+      // bias of the tile's 256 columns, spread over the lanes (lane l holds columns 32k + l); fetched before the accumulator wait,
+      // handed to every row with shuffles: a load inside the chunk loop would put an L2 round trip on each chunk's critical path
+      const bool add_bias = p.bias != nullptr && split == 0;
+      float breg[PBN / 32];
+#pragma unroll
+      for (int k = 0; k < PBN / 32; ++k) {
+        const int col = n0 + 32 * k + lane;
+        breg[k] = (add_bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      }
       if (!ptx::mbar_wait(ptx::smem_u32(&acc_full[a]), (ai >> 1) & 1)) { atomicExch(&g_sm100_error, 37); break; }
       ++ai;
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem + ((uint32_t)(q * 32) << 16) + a * PBN;
-      const bool add_bias = p.bias != nullptr && split == 0;
       const int row0 = m0 + q * 32;                                // first row of this warp's slab
       if (!p.out_bf16) {
         const int nchunk = min(PBN / 32, (p.N - n0 + 31) / 32);
-        for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+        for (int c = 0; c < PBN / 32; ++c) {
+          if (c >= nchunk) break;
           uint32_t r[32];
           ptx::tmem_ld_32x32(t_acc + (uint32_t)(c * 32), r);
           ptx::tc_wait_ld();
@@ -218,16 +228,8 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (add_bias) {
-            if (n + 32 <= p.N) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, breg[c], j);
           }
           if (lane == 0) ptx::p_bulk_wait_read1();                 // the store that used this staging box two chunks ago has read it
           __syncwarp();
@@ -253,7 +255,9 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         float ce_m = -INFINITY, ce_s = 0.f;
         long long ce_tgt = -1;
         if (p.ce_part && my_m < p.M) ce_tgt = p.ce_targets[p.ce_tmap(my_m)];
-        for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+        for (int c = 0; c < PBN / 64; ++c) {
+          if (c >= nchunk) break;
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32(t_acc + (uint32_t)(c * 64), r0);
           ptx::tmem_ld_32x32(t_acc + (uint32_t)(c * 64 + 32), r1);
@@ -269,7 +273,10 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
           if (add_bias) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] += (n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
+            for (int j = 0; j < 32; ++j) {
+              v[j] += __shfl_sync(0xffffffffu, breg[2 * c], j);
+              v[32 + j] += __shfl_sync(0xffffffffu, breg[2 * c + 1], j);
+            }
           }
           if (p.ce_part) {
             constexpr float LOG2E = 1.4426950408889634f;

@@ -101,13 +101,31 @@ class DataParallelTrainer:
         f = optimizer._ensure_flat()
         names = [n for n, _ in model.named_parameters()]
         sizes = [p.numel() for p in f["params"]]
-        self.reducer = GradAllReducer(f["g"], bucket_ranges(names, f["offsets"], sizes), group=group, overlap=overlap)
-        optimizer.attach(model, on_bucket_ready=self.reducer.ready)
+        self.ranges = bucket_ranges(names, f["offsets"], sizes)
+        self.reducer = GradAllReducer(f["g"], self.ranges, group=group, overlap=overlap)
+        # Adam per bucket, right behind that bucket's all-reduce: needs gradients that backward writes in place (CUDA path)
+        self.early_adam = f["g"].is_cuda
+        optimizer.attach(model, on_bucket_ready=self._bucket_ready)
+
+    def _bucket_ready(self, bucket: str) -> None:
+        """Called by backward once every kernel producing `bucket`'s gradients has been enqueued (and nothing later in the step
+        reads that bucket's weights): all-reduce it, then update it, both beside the rest of backward."""
+        self.reducer.ready(bucket)
+        if not self.early_adam:
+            return
+        a, b = self.ranges[bucket]
+        a, b = a // 8 * 8, (b + 7) // 8 * 8
+        if self.reducer.overlap:
+            with torch.cuda.stream(self.reducer.comm_stream):        # stream order: after this bucket's all-reduce
+                self.opt.step_range(a, b)
+        else:
+            self.opt.step_range(a, b)
 
     def step(self, feats, targets, mask=None):
         self.opt.zero_grad(set_to_none=True)
         loss = self.model.forward_loss(feats, targets, mask)
+        self.opt.begin_step()
         loss.backward()
         self.reducer.finish()
-        self.opt.step()
+        self.opt.finish_step()
         return loss

@@ -225,13 +225,14 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     dg2 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
     dout1 = torch.empty(T * B, H, device=dev)
     dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
-    ev_dout2, ev_dg2, ev_dg1 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    ev_dout2, ev_dg2, ev_dout1, ev_dg1 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     with torch.cuda.stream(chain):
         gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
         ev_dout2.record(chain)
         lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
         ev_dg2.record(chain)
         gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
+        ev_dout1.record(chain)
         lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
         ev_dg1.record(chain)
     # ---- out_linear:  dW = dl^T h,  db = colsum(dl)   (beside the word_rnn sweep; released together with it)
@@ -253,9 +254,10 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H, short_ctas=True)
     colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
     G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
-    _ready("word_rnn")
     demb = torch.empty(R, E, device=dev)
     gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True)
+    cur.wait_event(ev_dout1)
+    _ready("word_rnn")                                                          # (after the last readers of word_rnn's weights)
     gE.zero_()
     ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
     G["embedding.weight"] = gE
@@ -270,18 +272,18 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gb1, gb1b = _new("vid_rnn.bias_ih_l0", 4 * H), _new("vid_rnn.bias_hh_l0", 4 * H)
     colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1, gb1b)
     G.update({"vid_rnn.weight_ih_l0": gWih1, "vid_rnn.weight_hh_l0": gWhh1, "vid_rnn.bias_ih_l0": gb1, "vid_rnn.bias_hh_l0": gb1b})
-    _ready("vid_rnn")
     # ---- feat_linear: d xproj written back in batch-major row order so that it lines up with the bf16 features
     dxp = torch.empty(B * Lq, H, dtype=BF, device=dev)
     gemm(Lq * B, H, 4 * H, dg1, 4 * H, False, S["vid_rnn.weight_ih_l0"], H, True, dxp, rowmap(B, H, Lq * H), out_bf16=True)
+    _ready("vid_rnn")                                                           # (after the last reader of vid_rnn's weights)
     gWf = _new("feat_linear.weight", H, F)
     gemm(H, F, B * Lq, dxp, H, True, saved["xb"], F, True, gWf, dense(F))
     gbf = _new("feat_linear.bias", H)
     colsum_bf16(dxp, B * Lq, H, H, gbf)
     G.update({"feat_linear.weight": gWf, "feat_linear.bias": gbf})
-    _ready("feat_linear")
     if need_dfeats:                                                              # dataloader.py:38 makes feats require grad
         dfeats = torch.empty(B, Lq, F, device=dev)
         gemm(B * Lq, F, H, dxp, H, False, S["feat_linear.weight"], F, True, dfeats, dense(F))
         G["feats"] = dfeats
+    _ready("feat_linear")
     return G

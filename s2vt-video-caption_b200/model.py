@@ -180,9 +180,9 @@ def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_majo
     gb = _new("out_linear.bias", V)
     ops.colsum_f32(dl, R, V, V, gb)
     G["out_linear.bias"] = gb
-    _ready("out_linear")
     dout2 = torch.empty(T * B, H, device=dev)          # rows < L*B are never read (dout_t0 = L)
     ops.gemm_f32(R, H, V, dl, amap_rows, False, P["out_linear.weight"], dense(H), True, dout2, dense(H), c_off=hdec_off)
+    _ready("out_linear")                               # on_ready may update the bucket's weights: only after their last reader
     # ---- word_rnn
     dg2 = torch.empty(T * B, 4 * H, device=dev)
     ops.lstm_bwd_f32(T, B, H, L, dout2, saved["g2"], saved["c2"], P["word_rnn.weight_hh_l0"], dg2)
@@ -199,13 +199,13 @@ def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_majo
     gb2b = _new("word_rnn.bias_hh_l0", 4 * H)
     ops.colsum_f32(dg2, T * B, 4 * H, 4 * H, gb2b)
     G["word_rnn.bias_hh_l0"] = gb2b
-    _ready("word_rnn")
     # d input2 = dg2 . W_ih2: vid half -> dL/d output1, embedding half -> dense embedding grad
     dout1 = torch.empty(T * B, H, device=dev)
     ops.gemm_f32(T * B, H, 4 * H, dg2, dense(4 * H), False, P["word_rnn.weight_ih_l0"], dense(E + H), True, dout1, dense(H), b_off=E)
     demb = torch.empty(R, E, device=dev)
     ops.gemm_f32(R, E, 4 * H, dg2, dense(4 * H), False, P["word_rnn.weight_ih_l0"], dense(E + H), True, demb, dense(E),
                  a_off=L * B * 4 * H)
+    _ready("word_rnn")
     gE = _new("embedding.weight", V, E)
     gE.zero_()
     ops.embed_scatter_add_f32(gE, targets, 0, L - 1, B, L - 1, demb, E)
@@ -226,21 +226,21 @@ def train_backward_f32(P, saved, feats, targets, dl: torch.Tensor, dl_batch_majo
     gb1b = _new("vid_rnn.bias_hh_l0", 4 * H)
     ops.colsum_f32(dg1, T * B, 4 * H, 4 * H, gb1b)
     G["vid_rnn.bias_hh_l0"] = gb1b
-    _ready("vid_rnn")
     # ---- feat_linear
     dxp = torch.empty(L * B, H, device=dev)
     ops.gemm_f32(L * B, H, 4 * H, dg1, dense(4 * H), False, P["vid_rnn.weight_ih_l0"], dense(H), True, dxp, dense(H))
+    _ready("vid_rnn")
     gWf = _new("feat_linear.weight", H, F)
     ops.gemm_f32(H, F, L * B, dxp, dense(H), True, feats, rowmap(B, F, L * F), True, gWf, dense(F))
     G["feat_linear.weight"] = gWf
     gbf = _new("feat_linear.bias", H)
     ops.colsum_f32(dxp, L * B, H, H, gbf)
     G["feat_linear.bias"] = gbf
-    _ready("feat_linear")
     dfeats = None
     if need_dfeats:                                     # dataloader.py:38 makes feats require grad
         dfeats = torch.empty(B, L, F, device=dev)
         ops.gemm_f32(L * B, F, H, dxp, dense(H), False, P["feat_linear.weight"], dense(F), True, dfeats, rowmap(B, F, L * F))
+    _ready("feat_linear")
     return [G[k] for k in PARAM_ORDER], dfeats
 
 

@@ -81,6 +81,35 @@ class FusedAdam(torch.optim.Optimizer):
             return None
         return {n: f["shadow"][o:o + p.numel()].view(p.shape) for (n, p), o in zip(named_params, f["offsets"])}
 
+    # ---- bucket-wise stepping: Adam on a slice of the flat buffer as soon as that slice's gradient is final, so that most of
+    # the (HBM-bound) update runs beside the BPTT sweeps instead of after them.  begin_step() / step_range()* / finish_step().
+    @torch.no_grad()
+    def begin_step(self) -> None:
+        f = self._ensure_flat()
+        f["step"] += 1
+        f["stepped"] = []
+
+    @torch.no_grad()
+    def step_range(self, a: int, b: int, grad_scale: float = 1.0) -> None:
+        """Adam on flat elements [a, b) (a multiple of 8) with this step's bias correction; launches on the current stream."""
+        f = self._flat
+        group = self.param_groups[0]
+        ops.adam_f32(f["p"][a:b], f["g"][a:b], f["m"][a:b], f["v"][a:b], float(group["lr"]), float(group["betas"][0]),
+                     float(group["betas"][1]), float(group["eps"]), f["step"], grad_scale=grad_scale, bf16_copy=f["shadow"][a:b])
+        f["stepped"].append((a, b))
+
+    @torch.no_grad()
+    def finish_step(self, grad_scale: float = 1.0) -> None:
+        """Steps whatever begin_step()/step_range() has not covered yet and marks the bf16 shadows current."""
+        f = self._flat
+        pos = 0
+        for a, b in sorted(f["stepped"]) + [(f["n"], f["n"])]:
+            if a > pos:
+                self.step_range(pos, a, grad_scale)
+            pos = max(pos, b)
+        f["stepped"] = []
+        f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = None

@@ -40,11 +40,15 @@ SHAPES = [  # name, M, N, K, a_mn, b_mn, out_bf16, bias
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="", help="substring filter on the shape name")
+    ap.add_argument("--persistent-only", action="store_true")
     args = ap.parse_args()
     lib = s2vt_b200.load()
     dev = torch.device("cuda:0")
     tot = {0: 0.0, 1: 0.0}
     for name, M, N, K, a_mn, b_mn, obf, has_bias in SHAPES:
+        if args.only and args.only not in name:
+            continue
         nbytes = 2 * (M * K + N * K) + (2 if obf else 4) * M * N
         ncopy = max(2, min(8, int(300e6 // nbytes) + 1))
         As = [torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16() for _ in range(ncopy)]
@@ -52,7 +56,7 @@ def main():
         Cs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if obf else torch.float32) for _ in range(ncopy)]
         bias = torch.randn(N, device=dev) if has_bias else None
         res = {}
-        for persistent in (1, 0):
+        for persistent in ((1,) if args.persistent_only else (1, 0)):
             lib.s2vt_gemm_bf16_set_mode(0, persistent)
 
             def run(i):
@@ -73,6 +77,7 @@ def main():
             us = 1e3 * e0.elapsed_time(e1) / args.iters
             res[persistent] = us
             tot[persistent] += us
+        res.setdefault(0, float("nan"))
         lib.s2vt_gemm_bf16_set_mode(0, 1)
         fl = 2.0 * M * N * K
         print(json.dumps({"gemm": name, "M": M, "N": N, "K": K, "layout": "%s%s" % ("T" if a_mn else "N", "T" if b_mn else "N"),
