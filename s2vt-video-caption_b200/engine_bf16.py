@@ -28,7 +28,9 @@ def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None
          short_ctas=False):
     """short_ctas: use the one-tile-per-CTA kernel.  Required for products that run BESIDE a recurrence sweep: a persistent CTA
     keeps its SM for the whole product, and the sweep's 16-CTA clusters could not be placed until it retires."""
-    tag = "gemm_bf16[%dx%dx%d %s%s%s]" % (M, N, K, "T" if a_mn else "N", "T" if b_mn else "N", " bf16out" if out_bf16 else "")
+    persistent = not short_ctas and cmap.inner == 1 and cmap.stride_inner == 0         # the library routes dense outputs there
+    tag = "gemm_bf16_%s[%dx%dx%d %s%s%s]" % ("persist" if persistent else "tile", M, N, K, "T" if a_mn else "N", "T" if b_mn else "N",
+                                             " bf16out" if out_bf16 else "")
     lib = L.load()
     if short_ctas:
         lib.s2vt_gemm_bf16_set_mode(0, 0)
@@ -132,7 +134,7 @@ def vocab_ce_fwd(R, V, K, A, a_off, W, bias, targets_full, t_off, tmap, loss):
     ztgt = torch.empty(R, device=dev)
     lse = torch.empty(R, device=dev)
     row_loss = torch.empty(R, device=dev)
-    with ops._timed("gemm_bf16[%dx%dx%d NN bf16out +CE]" % (R, V, K), 2.0 * R * V * K, 2.0 * (R * K + V * K) + 2.0 * R * V):
+    with ops._timed("gemm_bf16_persist[%dx%dx%d NN bf16out +CE]" % (R, V, K), 2.0 * R * V * K, 2.0 * (R * K + V * K) + 2.0 * R * V):
         rc = lib.s2vt_vocab_ce_fwd_bf16(L.stream_ptr(dev), R, V, K, L.ptr(A, a_off), K, L.ptr(W), K, L.ptr(bias), L.ptr(logits), V,
                                         L.ptr(targets_full, t_off), tmap, L.ptr(part), L.ptr(ztgt), L.ptr(lse), L.ptr(row_loss), L.ptr(loss))
     L.check(rc, "s2vt_vocab_ce_fwd_bf16")
