@@ -115,6 +115,13 @@ int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
                        const float* h0, const float* c0,
                        void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT);
 
+/* As above with a direction flag: reverse = 1 makes processing step s read pre / write out and the stash at time index T-1-s,
+ * i.e. the reverse direction of a bidirectional nn.LSTM (attention_baseline.py:23) on time-ordered buffers, with no reversed copies. */
+int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_pre,
+                           const float* pre, const float* bias_sum, const void* w_hh_bf16,
+                           const float* h0, const float* c0,
+                           void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse);
+
 /* Persistent tensor-core BPTT, the backward twin of s2vt_lstm_fwd_bf16 (same cluster shape; needs H % 128 == 0, H <= 512).
  *   dout [T,B,H] f32 (rows t < dout_t0 are zero and never read) or NULL;  gates_bf16 / cells: the forward stash (private layout)
  *   w_hh_t_bf16 [H,4H] bf16 = W_hh transposed;  dgates_bf16 [T,B,4H] bf16 out (time-major GEMM layout)
@@ -122,6 +129,10 @@ int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
 int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0,
                        const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
                        void* dgates_bf16);
+
+int s2vt_lstm_bwd_bf16_dir(void* stream, int T, int B, int H, int dout_t0,
+                           const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
+                           void* dgates_bf16, int reverse);
 
 /* BPTT through one layer from a zero final-state gradient.
  *   dout   [T, B, H]  dL/dh_t from above; rows t < dout_t0 are treated as zero (and not read)

@@ -20,9 +20,13 @@ from typing import Dict
 import torch
 from torch import nn
 
+from . import engine_bf16 as EB
+from . import lib as L
 from . import ops
 from .lib import dense, require_cuda, rowmap
 from .model import _LinearParams
+
+BF = torch.bfloat16
 
 ATT_PARAM_ORDER = (
     "encoder.weight_ih_l0", "encoder.weight_hh_l0", "encoder.bias_ih_l0", "encoder.bias_hh_l0",
@@ -222,6 +226,169 @@ def att_backward_f32(P, saved, feats, targets, dl, need_dfeats: bool):
     return G, dfeats
 
 
+# --------------------------------------------------------------------------- tensor-core (bf16) engine
+class _AttShadows:
+    """bf16 mirrors of the weights (+ W_hh^T for the BPTT kernels, summed LSTM biases); rebuilt when a weight changes."""
+
+    def __init__(self):
+        self.key, self.t = None, {}
+
+    def get(self, P):
+        key = (ops.WEIGHT_EPOCH,) + tuple((p.data_ptr(), p._version) for p in P.values())
+        if key == self.key:
+            return self.t
+        t = {}
+        for name in ("feat_linear.weight", "encoder.weight_ih_l0", "encoder.weight_ih_l0_reverse", "decoder.weight_ih_l0", "out_linear.weight",
+                     "embedding.weight"):
+            t[name] = EB.cast(P[name], P[name].shape[0], P[name].shape[1])[0]
+        for name in ("encoder.weight_hh_l0", "encoder.weight_hh_l0_reverse", "decoder.weight_hh_l0"):
+            t[name], t[name + ".T"] = EB.cast(P[name], P[name].shape[0], P[name].shape[1], want_t=True)
+        t["b"] = _sum_bias(P, "encoder")
+        t["b_reverse"] = _sum_bias(P, "encoder", "_reverse")
+        t["b_dec"] = _sum_bias(P, "decoder")
+        self.key, self.t = key, t
+        return t
+
+
+def att_bf16_supported(H, E, F, V):
+    return EB.supported(H, E, F, V)
+
+
+def att_forward_bf16(P, S, feats, targets, stash: bool):
+    """Att_Baseline.forward(mode='train') on tensor cores: every contraction a tcgen05 GEMM, the three recurrences (encoder forward,
+    encoder reverse via the direction flag, decoder) in the persistent cluster kernel.  Returns (fp32 logits [B,L-1,V], saved)."""
+    B, Lq, F = feats.shape
+    H = P["encoder.weight_hh_l0"].shape[1]
+    V, E = P["embedding.weight"].shape
+    dev = feats.device
+    R = (Lq - 1) * B
+    Bp = int(L.load().s2vt_lstm_bf16_batch_pad(B))
+    xb, _ = EB.cast(feats, B * Lq, F)                                              # batch-major rows (b, l)
+    xproj = torch.empty(Lq * B, H, dtype=BF, device=dev)                           # time-major rows (l, b)
+    EB.gemm(B * Lq, H, F, xb, F, False, S["feat_linear.weight"], F, False, xproj, rowmap(Lq, H, B * H), out_bf16=True,
+            bias=P["feat_linear.bias"])
+    enc = {}
+    for sfx in ("", "_reverse"):
+        pre = torch.empty(Lq * B, 4 * H, device=dev)
+        EB.gemm(Lq * B, 4 * H, H, xproj, H, False, S["encoder.weight_ih_l0" + sfx], H, False, pre, dense(4 * H), bias=S["b" + sfx])
+        out = torch.empty(Lq * B, H, dtype=BF, device=dev)                         # time order for both directions
+        g = torch.empty(Lq * Bp * 4 * H, dtype=BF, device=dev) if stash else None
+        c = torch.empty(Lq * Bp * H, device=dev) if stash else None
+        EB.lstm_fwd(Lq, B, H, Lq, pre, S["b" + sfx], S["encoder.weight_hh_l0" + sfx], out, g, c, reverse=(sfx != ""))
+        ctx = torch.empty(B, H, device=dev)                                        # sum over frames (attention weights are all 1)
+        EB.colsum_bf16(out, Lq, B * H, B * H, ctx)
+        enc[sfx] = (out, g, c, EB.cast(ctx, B, H)[0])
+    Wd = S["decoder.weight_ih_l0"]
+    ctx_pre = torch.empty(B, 4 * H, device=dev)
+    EB.gemm(B, 4 * H, H, enc[""][3], H, False, Wd, E + 2 * H, False, ctx_pre, dense(4 * H), bias=S["b_dec"], b_off=E)
+    EB.gemm(B, 4 * H, H, enc["_reverse"][3], H, False, Wd, E + 2 * H, False, ctx_pre, dense(4 * H), accumulate=True, b_off=E + H)
+    emb_seq = torch.empty(R, E, dtype=BF, device=dev)
+    rc = L.load().s2vt_embed_gather_bf16(L.stream_ptr(dev), L.ptr(S["embedding.weight"]), E, L.ptr(targets), Lq - 1, B, Lq - 1, L.ptr(emb_seq), E)
+    L.check(rc, "s2vt_embed_gather_bf16")
+    pre_d = torch.empty(R, 4 * H, device=dev)
+    ops.bcast_rows_f32(ctx_pre, 0, 4 * H, B, 4 * H, Lq - 1, pre_d)
+    EB.gemm(R, 4 * H, E, emb_seq, E, False, Wd, E + 2 * H, False, pre_d, dense(4 * H), accumulate=True)
+    out_d = torch.empty(R, H, dtype=BF, device=dev)
+    g_d = torch.empty((Lq - 1) * Bp * 4 * H, dtype=BF, device=dev) if stash else None
+    c_d = torch.empty((Lq - 1) * Bp * H, device=dev) if stash else None
+    EB.lstm_fwd(Lq - 1, B, H, Lq - 1, pre_d, S["b_dec"], S["decoder.weight_hh_l0"], out_d, g_d, c_d)
+    logits = torch.empty(B, Lq - 1, V, device=dev)
+    EB.gemm(R, V, H, out_d, H, False, S["out_linear.weight"], H, False, logits, rowmap(B, V, (Lq - 1) * V), bias=P["out_linear.bias"])
+    saved = dict(xb=xb, xproj=xproj, enc=enc, emb_seq=emb_seq, out_d=out_d, g_d=g_d, c_d=c_d, dims=(B, Lq, F, H, E, V)) if stash else None
+    return logits, saved
+
+
+def att_backward_bf16(P, S, saved, targets, dl_bf, need_dfeats: bool):
+    """BPTT for att_forward_bf16; dl_bf = dL/dlogits as bf16 [(L-1)B, V] in time-major row order."""
+    B, Lq, F, H, E, V = saved["dims"]
+    dev = dl_bf.device
+    R = (Lq - 1) * B
+    out_d, enc, xproj, xb = saved["out_d"], saved["enc"], saved["xproj"], saved["xb"]
+    G = {}
+    new = lambda *s: torch.empty(*s, device=dev)                                    # noqa: E731
+    G["out_linear.weight"] = new(V, H)
+    EB.gemm(V, H, R, dl_bf, V, True, out_d, H, True, G["out_linear.weight"], dense(H))
+    G["out_linear.bias"] = new(V)
+    EB.colsum_bf16(dl_bf, R, V, V, G["out_linear.bias"])
+    dout_d = new(R, H)
+    EB.gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout_d, dense(H))
+    dg_d = torch.empty(R, 4 * H, dtype=BF, device=dev)
+    EB.lstm_bwd(Lq - 1, B, H, 0, dout_d, saved["g_d"], saved["c_d"], S["decoder.weight_hh_l0.T"], dg_d)
+    Wd = S["decoder.weight_ih_l0"]
+    dctx_pre = new(B, 4 * H)                                                         # the context feeds every decode step
+    EB.colsum_bf16(dg_d, Lq - 1, B * 4 * H, B * 4 * H, dctx_pre)
+    dctx_pre_bf = EB.cast(dctx_pre, B, 4 * H)[0]
+    gWd = new(4 * H, E + 2 * H)
+    EB.gemm(4 * H, E, R, dg_d, 4 * H, True, saved["emb_seq"], E, True, gWd, dense(E + 2 * H))
+    EB.gemm(4 * H, H, B, dctx_pre_bf, 4 * H, True, enc[""][3], H, True, gWd, dense(E + 2 * H), c_off=E)
+    EB.gemm(4 * H, H, B, dctx_pre_bf, 4 * H, True, enc["_reverse"][3], H, True, gWd, dense(E + 2 * H), c_off=E + H)
+    G["decoder.weight_ih_l0"] = gWd
+    G["decoder.weight_hh_l0"] = new(4 * H, H)
+    EB.gemm(4 * H, H, (Lq - 2) * B, dg_d, 4 * H, True, out_d, H, True, G["decoder.weight_hh_l0"], dense(H), a_off=B * 4 * H)
+    G["decoder.bias_ih_l0"], G["decoder.bias_hh_l0"] = new(4 * H), new(4 * H)
+    EB.colsum_bf16(dg_d, R, 4 * H, 4 * H, G["decoder.bias_ih_l0"], G["decoder.bias_hh_l0"])
+    demb = new(R, E)
+    EB.gemm(R, E, 4 * H, dg_d, 4 * H, False, Wd, E + 2 * H, True, demb, dense(E))
+    gE = new(V, E)
+    gE.zero_()
+    ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
+    gE[0].zero_()                                                                    # padding_idx=0
+    G["embedding.weight"] = gE
+    # ---- encoder: d enc_outputs[:, l] = d context for every frame; each direction contributes to d xproj
+    gWf, gbf = new(H, F), new(H)
+    dfeats = new(B, Lq, F) if need_dfeats else None
+    for i, (sfx, col) in enumerate((("", E), ("_reverse", E + H))):
+        out, g, c, _ = enc[sfx]
+        rev = sfx != ""
+        dctx = new(B, H)
+        EB.gemm(B, H, 4 * H, dctx_pre_bf, 4 * H, False, Wd, E + 2 * H, True, dctx, dense(H), b_off=col)
+        dout = new(Lq * B, H)
+        ops.bcast_rows_f32(dctx, 0, H, B, H, Lq, dout)
+        dg = torch.empty(Lq * B, 4 * H, dtype=BF, device=dev)
+        EB.lstm_bwd(Lq, B, H, 0, dout, g, c, S["encoder.weight_hh_l0" + sfx + ".T"], dg, reverse=rev)
+        gWih, gWhh = new(4 * H, H), new(4 * H, H)
+        EB.gemm(4 * H, H, Lq * B, dg, 4 * H, True, xproj, H, True, gWih, dense(H))
+        # previous hidden state in PROCESSING order: time t-1 for the forward direction, t+1 for the reverse one
+        EB.gemm(4 * H, H, (Lq - 1) * B, dg, 4 * H, True, out, H, True, gWhh, dense(H), a_off=0 if rev else B * 4 * H, b_off=B * H if rev else 0)
+        G["encoder.weight_ih_l0" + sfx], G["encoder.weight_hh_l0" + sfx] = gWih, gWhh
+        G["encoder.bias_ih_l0" + sfx], G["encoder.bias_hh_l0" + sfx] = new(4 * H), new(4 * H)
+        EB.colsum_bf16(dg, Lq * B, 4 * H, 4 * H, G["encoder.bias_ih_l0" + sfx], G["encoder.bias_hh_l0" + sfx])
+        dxp = torch.empty(B * Lq, H, dtype=BF, device=dev)                            # batch-major rows, lines up with xb
+        EB.gemm(Lq * B, H, 4 * H, dg, 4 * H, False, S["encoder.weight_ih_l0" + sfx], H, True, dxp, rowmap(B, H, Lq * H), out_bf16=True)
+        EB.gemm(H, F, B * Lq, dxp, H, True, xb, F, True, gWf, dense(F), accumulate=(i > 0))
+        if i == 0:
+            EB.colsum_bf16(dxp, B * Lq, H, H, gbf)
+        else:
+            part = new(H)
+            EB.colsum_bf16(dxp, B * Lq, H, H, part)
+            ops.add_f32(gbf, part, gbf)
+        if need_dfeats:
+            EB.gemm(B * Lq, F, H, dxp, H, False, S["feat_linear.weight"], F, True, dfeats, dense(F), accumulate=(i > 0))
+    G["feat_linear.weight"], G["feat_linear.bias"] = gWf, gbf
+    for k in _ATT_ZERO_GRAD:
+        G[k] = torch.zeros_like(P[k])
+    return G, dfeats
+
+
+class _AttTrainBf16Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, feats, targets, *params):
+        P = dict(zip(ATT_PARAM_ORDER, params))
+        need = any(ctx.needs_input_grad)
+        ctx.S = module._shadow.get(P)
+        logits, saved = att_forward_bf16(P, ctx.S, feats, targets, stash=need)
+        ctx.saved, ctx.P, ctx.targets = saved, P, targets
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        B, Lm1, V = dl.shape
+        dl_tm = dl.transpose(0, 1).contiguous().view(Lm1 * B, V).to(torch.bfloat16)    # layout glue for the caller-supplied gradient
+        G, dfeats = att_backward_bf16(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1])
+        ctx.saved = None
+        return (None, dfeats, None) + tuple(G[k] for k in ATT_PARAM_ORDER)
+
+
 class _AttTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, targets, *params):
@@ -239,8 +406,13 @@ class _AttTrainFn(torch.autograd.Function):
 
 
 class Att_Baseline(nn.Module):
-    def __init__(self, vocab_size, dim_feat, length, dim_hid=500, dim_embed=500, feat_dropout=0, out_dropout=0, sos_ix=3, eos_ix=4):
+    def __init__(self, vocab_size, dim_feat, length, dim_hid=500, dim_embed=500, feat_dropout=0, out_dropout=0, sos_ix=3, eos_ix=4,
+                 train_precision: str = "auto"):
         super().__init__()
+        if train_precision not in ("auto", "bf16", "fp32"):
+            raise ValueError("train_precision must be 'auto', 'bf16' or 'fp32'")
+        self.train_precision = train_precision
+        self._shadow = _AttShadows()
         if feat_dropout or out_dropout:
             raise NotImplementedError("dropout > 0 is not supported on the sm_100a path (the reference defaults are 0)")
         self.dim_feat = dim_feat
@@ -259,6 +431,18 @@ class Att_Baseline(nn.Module):
         self.att_enc = _LinearParams(dim_hid * 2, dim_hid)
         self.att_prev_hid = _LinearParams(dim_hid, dim_hid)
         self.att_apply = _LinearNoBias(dim_hid, 1)
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_shadow"] = _AttShadows()
+        return st
+
+    def _use_bf16(self) -> bool:
+        ok = att_bf16_supported(self.dim_hid, self.dim_embed, self.dim_feat, self.vocab_size) and self.length >= 3
+        if self.train_precision == "bf16" and not ok:
+            raise NotImplementedError("train_precision='bf16' needs dim_hid % 128 == 0, dim_hid <= 512 and dim_embed, dim_feat, "
+                                      "vocab_size multiples of 8; use train_precision='fp32' for other shapes")
+        return ok and self.train_precision != "fp32"
 
     def _params(self) -> Dict[str, torch.Tensor]:
         sd = dict(self.named_parameters())
@@ -279,6 +463,8 @@ class Att_Baseline(nn.Module):
                 raise RuntimeError("mode='train' needs targets [B, >= length-1] (attention_baseline.py:73-75)")
             t = targets[:, :self.length - 1].contiguous().to(torch.int64)           # the loop only reads columns < L-1
             P = self._params()
+            if self._use_bf16():
+                return _AttTrainBf16Fn.apply(self, feats, t, *[P[k] for k in ATT_PARAM_ORDER])
             return _AttTrainFn.apply(feats, t, *[P[k] for k in ATT_PARAM_ORDER])
         elif mode == 'test':
             with torch.no_grad():

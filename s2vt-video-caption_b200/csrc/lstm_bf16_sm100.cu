@@ -97,6 +97,7 @@ struct LstmFwdParams {
   float* cT;                       // [B,H] or null
   long long* trace;                // debug: [TRACE_STEPS][8] clock64 stamps of CTA 0, or null
   int dbg_flags;
+  int reverse;                     // 1: processing step s reads / writes time index T-1-s (the reverse direction of a bidirectional LSTM)
 };
 constexpr int TRACE_STEPS = 32, TRACE_T0 = 16;
 __device__ long long g_lstm_trace[TRACE_STEPS * 8];
@@ -265,7 +266,9 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
     const float* pre_row0 = p.pre + (long long)min(b0, p.B - 1) * 4 * H + g * H + unit;
     const int row_stride = (b0 + NB <= p.B) ? 4 * H : 0;               // ragged last tile: every column reads one valid row...
     const long long step_stride = (long long)p.B * 4 * H;
-    auto load_pre = [&](int t, float (&dst)[NB]) {
+    auto tm = [&](int s) { return p.reverse ? T - 1 - s : s; };               // processing step -> time index in global memory
+    auto load_pre = [&](int s, float (&dst)[NB]) {
+      const int t = tm(s);
       if (t < p.n_pre) {
         const float* src = pre_row0 + t * step_stride;
         if (row_stride != 0) {
@@ -357,8 +360,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       if (threadIdx.x == 0) S2VT_TRACE(6);
       // ---- off the critical path: h_t, c_t and the gate activations to HBM
       if (lane < NCH && b0 + bcol < p.B)
-        *reinterpret_cast<uint4*>(p.out + ((long long)t * p.B + b0 + bcol) * H + 32 * (int)c + 8 * m) = hchunk;
-      const long long blk = (long long)t * stash_blk + (long long)bt16 * CS + c;
+        *reinterpret_cast<uint4*>(p.out + ((long long)tm(t) * p.B + b0 + bcol) * H + 32 * (int)c + 8 * m) = hchunk;
+      const long long blk = (long long)tm(t) * stash_blk + (long long)bt16 * CS + c;
       if (p.cells) {
         float* cdst = p.cells + blk * (LSTM_NB * 32) + colbase * 32 + u;
 #pragma unroll
@@ -431,6 +434,13 @@ extern "C" int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
                                   const float* pre, const float* bias_sum, const void* w_hh_bf16,
                                   const float* h0, const float* c0,
                                   void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT) {
+  return s2vt_lstm_fwd_bf16_dir(stream, T, B, H, n_pre, pre, bias_sum, w_hh_bf16, h0, c0, out_bf16, gates_bf16, cells, hT, cT, 0);
+}
+
+extern "C" int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_pre,
+                                      const float* pre, const float* bias_sum, const void* w_hh_bf16,
+                                      const float* h0, const float* c0,
+                                      void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse) {
   S2VT_REQUIRE(T >= 1 && B >= 1, "s2vt_lstm_fwd_bf16: bad dims");
   S2VT_REQUIRE(H % 64 == 0 && H >= 64 && H <= 512, "s2vt_lstm_fwd_bf16: the cluster-resident kernel needs H %% 64 == 0 and 64 <= H <= 512 (got %d)", H);
   S2VT_REQUIRE(bias_sum && w_hh_bf16 && out_bf16, "s2vt_lstm_fwd_bf16: null pointer");
@@ -443,6 +453,7 @@ extern "C" int s2vt_lstm_fwd_bf16(void* stream, int T, int B, int H, int n_pre,
   p.out = (__nv_bfloat16*)out_bf16; p.gates = (__nv_bfloat16*)gates_bf16; p.cells = cells; p.hT = hT; p.cT = cT;
   p.trace = nullptr;
   p.dbg_flags = g_dbg_flags;
+  p.reverse = reverse ? 1 : 0;
   if (g_trace_enabled) {
     void* sym = nullptr;
     S2VT_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_lstm_trace));

@@ -30,6 +30,7 @@ struct LstmBwdParams {
   const float* cells;              // forward stash [T][nbt][CS][16][32]
   const __nv_bfloat16* w_t;        // W_hh^T bf16 [H, 4H]
   __nv_bfloat16* dgates;           // [T,B,4H] bf16 out
+  int reverse;                     // 1: processing step s <-> time index T-1-s in every global buffer (reverse direction of a BiLSTM)
 };
 
 __global__ void __launch_bounds__(160, 1)
@@ -140,11 +141,14 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
     int rowoff[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) rowoff[j] = min(b0 + q * CPT + j, p.B - 1);
-    auto load_step = [&](int t, bool first) {
-      const long long blk = (long long)t * stash_blk + my_blk0;
+    auto tm = [&](int s) { return p.reverse ? T - 1 - s : s; };
+    auto load_step = [&](int s, bool first) {
+      const int t = s;                                           // (processing step; `tt` below is its time index)
+      const int tt = tm(s);
+      const long long blk = (long long)tt * stash_blk + my_blk0;
       const uint2* gsrc = reinterpret_cast<const uint2*>(p.gates + blk * (NB * 32 * 4));
       const float* csrc = p.cells + blk * (NB * 32);
-      const float* cprev_src = p.cells + (blk - stash_blk) * (NB * 32);
+      const float* cprev_src = p.cells + ((long long)tm(s > 0 ? s - 1 : 0) * stash_blk + my_blk0) * (NB * 32);
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const int col = q * CPT + j;
@@ -152,7 +156,7 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
         if (first) c_t[j] = __ldg(csrc + col * 32 + u);
         else c_t[j] = c_prev[j];                                 // c_t of step t == c_{t-1} loaded for step t+1
         c_prev[j] = (t > 0) ? __ldg(cprev_src + col * 32 + u) : 0.f;
-        dout_v[j] = (p.dout && t >= p.dout_t0) ? __ldg(p.dout + ((long long)t * p.B + rowoff[j]) * H + unit) : 0.f;
+        dout_v[j] = (p.dout && tt >= p.dout_t0) ? __ldg(p.dout + ((long long)tt * p.B + rowoff[j]) * H + unit) : 0.f;
       }
     };
     load_step(T - 1, true);
@@ -274,7 +278,7 @@ lstm_bwd_cluster_kernel(const LstmBwdParams p) {
         const int x = threadIdx.x + 128 * r;
         const int kblk = x >> 4, b = x & 15;
         if (b0 + b < p.B)
-          *reinterpret_cast<uint4*>(p.dgates + ((long long)t * p.B + b0 + b) * 4 * H + (kblk >> 2) * H + 32 * (int)c + 8 * (kblk & 3)) = dgv4[r];
+          *reinterpret_cast<uint4*>(p.dgates + ((long long)tm(t) * p.B + b0 + b) * 4 * H + (kblk >> 2) * H + 32 * (int)c + 8 * (kblk & 3)) = dgv4[r];
       }
     }
   }
@@ -292,6 +296,12 @@ using namespace s2vt;
 extern "C" int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0,
                                   const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
                                   void* dgates_bf16) {
+  return s2vt_lstm_bwd_bf16_dir(stream, T, B, H, dout_t0, dout, gates_bf16, cells, w_hh_t_bf16, dgates_bf16, 0);
+}
+
+extern "C" int s2vt_lstm_bwd_bf16_dir(void* stream, int T, int B, int H, int dout_t0,
+                                      const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
+                                      void* dgates_bf16, int reverse) {
   S2VT_REQUIRE(T >= 1 && B >= 1, "s2vt_lstm_bwd_bf16: bad dims");
   S2VT_REQUIRE(H % 128 == 0 && H >= 128 && H <= 512, "s2vt_lstm_bwd_bf16: the cluster-resident kernel needs H %% 128 == 0 and 128 <= H <= 512 (got %d)", H);
   S2VT_REQUIRE(gates_bf16 && cells && w_hh_t_bf16 && dgates_bf16, "s2vt_lstm_bwd_bf16: null pointer");
@@ -300,6 +310,7 @@ extern "C" int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0
   p.T = T; p.B = B; p.H = H; p.dout_t0 = dout_t0 < 0 ? 0 : dout_t0;
   p.dout = dout; p.gates = (const __nv_bfloat16*)gates_bf16; p.cells = cells; p.w_t = (const __nv_bfloat16*)w_hh_t_bf16;
   p.dgates = (__nv_bfloat16*)dgates_bf16;
+  p.reverse = reverse ? 1 : 0;
   const int CS = H / 32;
   const size_t smem_need = 1024 + 2 * (size_t)CS * 32 * BWD_NB * 2 + (size_t)BWD_NB * 128 * 2;
   // keep GEMM CTAs of other streams (97 KB each) off the SMs of the cluster: this CTA owns the SM's tensor memory

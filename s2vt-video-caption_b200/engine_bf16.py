@@ -53,17 +53,17 @@ def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False, want_pla
     return dst, dst_t
 
 
-def lstm_fwd(T, B, H, n_pre, pre, bias_sum, w_bf, out, gates, cells, hT=None, cT=None, h0=None, c0=None):
+def lstm_fwd(T, B, H, n_pre, pre, bias_sum, w_bf, out, gates, cells, hT=None, cT=None, h0=None, c0=None, reverse=False):
     with ops._timed("lstm_fwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 4 * H + 2.0 * T * B * 6 * H):
-        rc = L.load().s2vt_lstm_fwd_bf16(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre), L.ptr(bias_sum), L.ptr(w_bf), L.ptr(h0),
-                                         L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT))
+        rc = L.load().s2vt_lstm_fwd_bf16_dir(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre), L.ptr(bias_sum), L.ptr(w_bf), L.ptr(h0),
+                                             L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT), int(reverse))
     L.check(rc, "s2vt_lstm_fwd_bf16")
 
 
-def lstm_bwd(T, B, H, dout_t0, dout, gates, cells, w_t_bf, dgates):
+def lstm_bwd(T, B, H, dout_t0, dout, gates, cells, w_t_bf, dgates, reverse=False):
     with ops._timed("lstm_bwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 3 * H + 2.0 * T * B * 8 * H):
-        rc = L.load().s2vt_lstm_bwd_bf16(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
-                                         L.ptr(w_t_bf), L.ptr(dgates))
+        rc = L.load().s2vt_lstm_bwd_bf16_dir(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
+                                             L.ptr(w_t_bf), L.ptr(dgates), int(reverse))
     L.check(rc, "s2vt_lstm_bwd_bf16")
 
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "s2vt_lstm_bf16_batch_pad": (_i64, [_i]),
     "s2vt_lstm_fwd_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2vt_lstm_bwd_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "s2vt_lstm_fwd_bf16_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "s2vt_lstm_bwd_bf16_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "s2vt_lstm_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2vt_embed_gather_f32": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),
     "s2vt_embed_scatter_add_f32": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),

@@ -24,8 +24,8 @@ def dev():
     return torch.device("cuda:0")
 
 
-def build(c, P, dev):
-    m = s2vt_b200.Att_Baseline(c["V"], c["F"], c["L"], dim_hid=c["H"], dim_embed=c["E"], sos_ix=3, eos_ix=4)
+def build(c, P, dev, precision="fp32"):
+    m = s2vt_b200.Att_Baseline(c["V"], c["F"], c["L"], dim_hid=c["H"], dim_embed=c["E"], sos_ix=3, eos_ix=4, train_precision=precision)
     m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in P.items()}, strict=True)
     return m.to(dev)
 
@@ -95,3 +95,55 @@ def test_att_vs_oracle_fresh_inputs(dev):
     if margins.min() > 1e-4:
         tok = build(c, P, dev)(torch.from_numpy(feats).to(dev), mode="test")
         assert np.array_equal(tok.cpu().numpy(), pred)
+
+
+def test_att_bf16_train_vs_oracle_fresh_inputs(dev):
+    """Tensor-core path on a small bf16-compatible shape (ragged batch: 24 = 16 + 8 columns) against the pinned numpy oracle.
+    Tolerances: loss rtol 1e-3; logits 1e-3*max(1,|z|max) + 3e-2*std(z) (the context is a SUM over frames rounded to bf16 before
+    the decoder's input product, which amplifies the operand rounding relative to S2VT's 1e-2*std); gradients rel-L2 <= 5e-2."""
+    V, F, H, E, L, B = 520, 64, 128, 64, 10, 24
+    P = A.synth_params(V, F, H, E, seed=911, out_scale=2.0, ctx_scale=0.3)
+    feats, targets, mask = O.synth_batch(B, L, F, V, seed=912, real_tokens=7)
+    c = dict(V=V, F=F, H=H, E=E, L=L, B=B)
+    logits, loss, grads = run_train(build(c, P, dev, "bf16"), feats, targets, mask, dev)
+    ref_logits, cache = A.forward_train(P, feats, targets[:, :-1], keep=True)
+    ref_grads = A.backward(P, cache, O.dlogits_of_loss(ref_logits, targets))
+    assert abs(loss - float(O.mask_criterion(ref_logits, targets, mask))) <= 1e-3 * abs(loss)
+    assert np.abs(logits - ref_logits).max() <= 1e-3 * max(1.0, float(np.abs(ref_logits).max())) + 3e-2 * float(ref_logits.std())
+    for k, gv in grads.items():
+        r = ref_grads[k]
+        if k.startswith("att_"):
+            assert not gv.any()
+            continue
+        rel = np.linalg.norm((gv - r).astype(np.float64)) / max(1e-30, np.linalg.norm(r.astype(np.float64)))
+        assert rel <= 5e-2, (k, rel)
+    assert not grads["embedding.weight"][0].any()
+
+
+@pytest.mark.parametrize("name", ["att_msvd"])
+def test_att_bf16_train_vs_reference_golden(dev, name):
+    """Tensor-core path (bf16 operands, fp32 accumulation) against the reference goldens: loss rtol 1e-3, logits
+    1e-3*max(1,|z|max) + 3e-2*std(z), gradient norms within 3e-2 (att_* layers exactly zero)."""
+    g = load_golden(name)
+    P, feats, targets, mask, c = att_golden_inputs(g)
+    logits, loss, grads = run_train(build(c, P, dev, "bf16"), feats, targets, mask, dev)
+    assert abs(loss - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    if "logits" in g:
+        ref = g["logits"]
+        assert np.abs(logits - ref).max() <= 1e-3 * max(1.0, float(np.abs(ref).max())) + 1e-2 * float(ref.std())
+        for k, gv in grads.items():
+            r = g["grad/" + k]
+            if k.startswith("att_"):
+                assert not gv.any()
+                continue
+            rel = np.linalg.norm((gv - r).astype(np.float64)) / max(1e-30, np.linalg.norm(r.astype(np.float64)))
+            assert rel <= 5e-2, (k, rel)
+    else:
+        ref = g["logits_sample"]
+        assert np.abs(logits.reshape(-1)[::STRIDE] - ref).max() <= 1e-3 * max(1.0, float(np.abs(ref).max())) + 3e-2 * float(ref.std())
+        for k, gv in grads.items():
+            if k.startswith("att_"):
+                assert not gv.any()
+                continue
+            n = np.linalg.norm(gv.astype(np.float64))
+            assert abs(n - g["grad_norm/" + k]) <= 3e-2 * g["grad_norm/" + k] + 1e-12, (k, n, g["grad_norm/" + k])
