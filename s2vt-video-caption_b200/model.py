@@ -464,6 +464,35 @@ class S2VT(nn.Module):
         P = self._params()
         return _TrainLossFn.apply(self, feats.contiguous(), targets.contiguous().to(torch.int64), *[P[k] for k in PARAM_ORDER])
 
+    # ---- pretrained word vectors (S2VTModel.py:112-147)
+    def load_glove_weights(self, glove_path, glove_dim, ix2word, word2embed=None):
+        """Re-initialise the embedding table from GloVe vectors: xavier-normal rows for words GloVe does not know, the GloVe vector
+        otherwise (S2VTModel.py:129-147; the table stays trainable, nn.Embedding.from_pretrained(freeze=False)).  `word2embed`: an
+        already-extracted {word: vector} dict or a JSON path (the reference caches one at ./data/word2embed.json); None parses
+        `glove_path` ("word v1 v2 ..." per line) for the words of `ix2word`."""
+        import json
+        assert glove_dim == self.dim_embed
+        if word2embed is None:
+            vocab = set(ix2word.values())
+            word2embed = {}
+            with open(glove_path, encoding="utf-8") as f:
+                for line in f:
+                    parts = line.rstrip().split(" ")
+                    if parts[0] in vocab:
+                        word2embed[parts[0]] = [float(x) for x in parts[1:]]
+        elif isinstance(word2embed, str):
+            with open(word2embed, encoding="utf-8") as fp:
+                word2embed = json.load(fp)
+        dev = self.embedding.weight.device
+        weights = torch.zeros([self.vocab_size, glove_dim], dtype=torch.float, device=dev)
+        torch.nn.init.xavier_normal_(weights)
+        for ix, word in ix2word.items():
+            if word in word2embed:
+                weights[int(ix)] = torch.tensor(word2embed[word], dtype=torch.float, device=dev)
+        with torch.no_grad():
+            self.embedding.weight.copy_(weights)
+        return len(word2embed)
+
     # ---- greedy (S2VTModel.py:82-110)
     def _greedy(self, feats):
         P = {k: v.detach() for k, v in self._params().items()}

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: Att_Baseline (attention_baseline.py) training throughput on one GPU or data-parallel under torchrun.
+One step = zero_grad + forward(mode='train') + MaskCriterion + backward + (gradient all-reduce) + FusedAdam.step, batch 64/GPU,
+MSVD shape (80 x 4096 features, V = 13000, H = E = 512), synthetic data, random-init weights.  Prints one JSON line.
+
+    python tools/bench_att.py [--steps 10] [--precision bf16|fp32]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import s2vt_b200
+from bench import CFG, synth_batch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default="bf16")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = s2vt_b200.Att_Baseline(CFG["V"], CFG["F"], CFG["L"], dim_hid=CFG["H"], dim_embed=CFG["E"], train_precision=args.precision).to(dev)
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-4)
+    crit = s2vt_b200.MaskCriterion()
+    flat_g = None
+    batches = [synth_batch(CFG["B"], 99 + rank * 10 + i, device=dev) for i in range(3)]
+
+    def step(i):
+        f, t, m = batches[i % 3]
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(f, targets=t[:, :-1], mode="train"), t, m)
+        loss.backward()
+        if world > 1:
+            for p in model.parameters():
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": "Att_Baseline train videos/sec", "value": round(world * CFG["B"] / (ms / 1e3), 1), "ms_per_step": round(ms, 3),
+                          "n_gpus": world, "precision": args.precision, "batch_per_gpu": CFG["B"], "loss": float(loss.item()),
+                          "launches_total": int(s2vt_b200.launch_count())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
