@@ -122,6 +122,10 @@ int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_pre,
                            const float* h0, const float* c0,
                            void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse);
 
+/* Tiles per cluster for the calling thread's subsequent recurrence launches: 1 (default) = one 16-column batch tile per cluster,
+ * 2 = two tiles share a cluster's resident weight slice (half the SMs per sweep: lets two layers' sweeps run side by side). */
+int s2vt_lstm_bf16_set_tiles_per_cluster(int n);
+
 /* Persistent tensor-core BPTT, the backward twin of s2vt_lstm_fwd_bf16 (same cluster shape; needs H % 128 == 0, H <= 512).
  *   dout [T,B,H] f32 (rows t < dout_t0 are zero and never read) or NULL;  gates_bf16 / cells: the forward stash (private layout)
  *   w_hh_t_bf16 [H,4H] bf16 = W_hh transposed;  dgates_bf16 [T,B,4H] bf16 out (time-major GEMM layout)

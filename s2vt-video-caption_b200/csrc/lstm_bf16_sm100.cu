@@ -103,6 +103,7 @@ constexpr int TRACE_STEPS = 32, TRACE_T0 = 16;
 __device__ long long g_lstm_trace[TRACE_STEPS * 8];
 static bool g_trace_enabled = false;
 static int g_last_max_clusters[2] = {-1, -1};   // [wide, narrow] result of cudaOccupancyMaxActiveClusters (debug)
+static thread_local int g_tiles_per_cluster = 1;   // 2: two batch tiles per cluster (half the SMs per sweep)
 static int g_dbg_flags = 0;                 // 8 = keep W in shared memory (the v1 data path) instead of TMEM
 #define S2VT_TRACE(slot)                                                                              \
   do {                                                                                                \
@@ -110,45 +111,61 @@ static int g_dbg_flags = 0;                 // 8 = keep W in shared memory (the 
       p.trace[(t - TRACE_T0) * 8 + (slot)] = clock64();                                               \
   } while (0)
 
-template <int NB, bool W_TMEM>
-__global__ void __launch_bounds__(160, 1)
+// NTL = batch tiles per cluster.  NTL = 2 runs two independent 16-column recurrences on the same resident weight slice, each with its
+// own four epilogue warps, barriers, h buffers and accumulator: while one tile's h_t is in flight through the cluster, the other
+// tile's MMAs / activations run, so the same sweep needs half the SMs (B = 64 -> 2 clusters instead of 4).
+template <int NB, bool W_TMEM, int NTL>
+__global__ void __launch_bounds__(32 * (4 * NTL + 1), 1)
 lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdParams p) {
-  static_assert(NB == 16 || NB == 8, "thread mapping below assumes 16 or 8 batch columns per cluster (4 or 2 per epilogue warp)");
+  static_assert(NB == 16 || NB == 8, "thread mapping below assumes 16 or 8 batch columns per tile (4 or 2 per epilogue warp)");
+  static_assert(NTL == 1 || (NTL == 2 && NB == 16 && W_TMEM), "two tiles per cluster: 16-column tiles, weights in tensor memory");
   constexpr int MN = LSTM_MN;
   constexpr int CPT = NB / 4;                       // phase-2 columns per thread
   constexpr int NCH = NB;                           // 16-byte h chunks (8 units x 1 column) produced per warp and step
   constexpr int PPL = NCH / 2;                      // peers each lane serves: 32 / NCH lanes share a chunk and split the 16 peers
+  constexpr int CTRL = 4 * NTL, EPI_THREADS = 128 * NTL;
   constexpr uint32_t LBO_H = (MN / 8) * 128;        // K-direction stride between 8x16B core matrices of h^T
   constexpr uint32_t SLICE_BYTES = 4 * LBO_H;       // one CTA's 32 hidden units x MN batch columns, bf16
   constexpr uint32_t XCHG_BYTES = 4 * (NB / 8) * 128;   // bytes of it that carry real columns and are exchanged
+  constexpr uint32_t TILE_SMEM = 2 * 4 * NB * 32 * 4 + 2 * NB * 32 * 4 * 2 + 4 * 256;   // sG + sSt + sPk of one tile
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t w_full, h_full[2], mma_done;
+  __shared__ __align__(8) uint64_t w_full, h_full[NTL][2], mma_done[NTL];
   __shared__ uint32_t tmem_slot;
 
   const int H = p.H, KC = H / 64, CS = H / 32;
   const uint32_t W_BYTES = W_TMEM ? 0u : 128u * (uint32_t)H * 2u, HBUF_BYTES = (uint32_t)MN * (uint32_t)H * 2u;
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sW = base, sH0 = sW + W_BYTES;
+  const uint32_t sW = base;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));            // generic pointer to the aligned base
-  uint8_t* gH0 = gen + W_BYTES;
-  float* sG = reinterpret_cast<float*>(gH0 + 2 * HBUF_BYTES);            // [2][4 gates][NB][32 units] fp32
-  __nv_bfloat16* sSt = reinterpret_cast<__nv_bfloat16*>(sG + 2 * 4 * NB * 32);   // [2][NB][32][4] bf16 stash staging
-  uint8_t* sPk = reinterpret_cast<uint8_t*>(sSt + 2 * NB * 32 * 4);      // [4 warps][16 chunks][16 B] h packing
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const int tl = warp < CTRL ? (warp >> 2) : 0;                           // batch tile served by this epilogue warp
+  const int wq = warp & 3;                                                // its TMEM lane quarter / gate / column group
   const uint32_t c = ptx::cluster_ctarank();                              // hidden-unit slice of this CTA
-  const int bt = blockIdx.x / CS, nbt = gridDim.x / CS;
-  const int b0 = bt * NB;                                                 // batch tile of this cluster
+  const int bt = blockIdx.x / CS;                                         // cluster index
   const int T = p.T;
   const uint32_t tmem_cols = W_TMEM ? (H >= 512 ? 512u : (H >= 256 ? 256u : (H >= 128 ? 128u : 64u))) : 32u;
+  // per-tile shared memory: [tile][2 h buffers] first (the MMA's B operands), then each tile's staging areas
+  const uint32_t sH_all = sW + W_BYTES;
+  uint8_t* gH_all = gen + W_BYTES;
+  const uint32_t sH0 = sH_all + (uint32_t)tl * 2 * HBUF_BYTES;
+  uint8_t* gH0 = gH_all + (size_t)tl * 2 * HBUF_BYTES;
+  uint8_t* gTile = gH_all + (size_t)NTL * 2 * HBUF_BYTES + (size_t)tl * TILE_SMEM;
+  float* sG = reinterpret_cast<float*>(gTile);                            // [2][4 gates][NB][32 units] fp32
+  __nv_bfloat16* sSt = reinterpret_cast<__nv_bfloat16*>(sG + 2 * 4 * NB * 32);   // [2][NB][32][4] bf16 stash staging
+  uint8_t* sPk = reinterpret_cast<uint8_t*>(sSt + 2 * NB * 32 * 4);      // [4 warps][16 chunks][16 B] h packing
+  const int b0 = (bt * NTL + tl) * NB;                                    // first batch column of this warp's tile
+  const bool tile_on = b0 < p.B;
 
-  if (warp == 4 && ptx::elect_one()) {
+  if (warp == CTRL && ptx::elect_one()) {
     if (!W_TMEM) ptx::prefetch_tmap(&tmW);
     ptx::mbar_init(ptx::smem_u32(&w_full), 1);
-    ptx::mbar_init(ptx::smem_u32(&h_full[0]), 1);
-    ptx::mbar_init(ptx::smem_u32(&h_full[1]), 1);
-    ptx::mbar_init(ptx::smem_u32(&mma_done), 1);
+    for (int i = 0; i < NTL; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&h_full[i][0]), 1);
+      ptx::mbar_init(ptx::smem_u32(&h_full[i][1]), 1);
+      ptx::mbar_init(ptx::smem_u32(&mma_done[i]), 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -156,8 +173,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
     ptx::tmem_relinquish();
   }
   // initial h^T buffer (step 0 input): zeros or h0 in the canonical layout
-  if (warp < 4) {
-    for (int idx = threadIdx.x; idx < MN * H / 8; idx += 128) {           // one 16-byte chunk (8 k-elements) per iteration
+  if (warp < CTRL) {
+    for (int idx = (int)threadIdx.x - 128 * tl; idx < MN * H / 8; idx += 128) {    // one 16-byte chunk (8 k-elements) per iteration
       const int kblk = idx / MN, b = idx % MN;
       uint4 v = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(gH0 + HBUF_BYTES + (size_t)(kblk * (MN / 8) + b / 8) * 128 + (b % 8) * 16) = v;   // idle columns stay 0
@@ -176,18 +193,19 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tmem_acc = W_TMEM ? tmem + (uint32_t)(H / 2) : tmem;     // accumulator columns sit after the weight columns
-  if (W_TMEM && warp < 4) {
-    // thread (gate g = warp, unit u = lane) owns TMEM lane 32g+u = gate row g*H + 32c + u of W_hh: two bf16 per 32-bit column
-    const uint4* src = reinterpret_cast<const uint4*>(p.w + ((long long)warp * H + 32 * (int)c + lane) * H);
-    for (int cc = 0; cc < H / 64; ++cc) {
+  const uint32_t tmem_acc0 = W_TMEM ? tmem + (uint32_t)(H / 2) : tmem;    // accumulator columns sit after the weight columns
+  const uint32_t tmem_acc = tmem_acc0 + (uint32_t)(tl * MN);
+  if (W_TMEM && warp < CTRL) {
+    // thread (gate g = wq, unit u = lane) owns TMEM lane 32g+u = gate row g*H + 32c + u of W_hh: two bf16 per 32-bit column
+    const uint4* src = reinterpret_cast<const uint4*>(p.w + ((long long)wq * H + 32 * (int)c + lane) * H);
+    for (int cc = tl; cc < H / 64; cc += NTL) {
       uint32_t r[32];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint4 v = __ldg(src + cc * 8 + i);
         r[4 * i + 0] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
       }
-      ptx::tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), r);
+      ptx::tmem_st_32x32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cc * 32), r);
     }
     ptx::tc_wait_st();
     ptx::tc_fence_before();
@@ -197,8 +215,8 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
   ptx::cluster_arrive();                                                  // every peer's barriers are initialised before
   ptx::cluster_wait();                                                    // anyone signals them remotely
 
-  if (warp == 4) {
-    // ===================== control thread: (weight load,) per-step MMA issue =====================
+  if (warp == CTRL) {
+    // ===================== control thread: (weight load,) per-step MMA issue for every tile =====================
     if (ptx::elect_one()) {
       bool ok = true;
       if (!W_TMEM) {
@@ -210,48 +228,56 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
         if (!ok) atomicExch(&g_sm100_error, 11);
       }
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, MN, 0, 0);
-      uint32_t ph[2] = {0, 0};
+      uint32_t ph[NTL][2];
+      bool on[NTL];
+      for (int i = 0; i < NTL; ++i) { ph[i][0] = ph[i][1] = 0; on[i] = (bt * NTL + i) * NB < p.B; }
       const bool have_h0 = p.h0 != nullptr;
-      const uint64_t db_base[2] = {ptx::make_smem_desc(sH0, LBO_H, 128, 0), ptx::make_smem_desc(sH0 + HBUF_BYTES, LBO_H, 128, 0)};
       for (int t = 0; t < T && ok; ++t) {
         const int pb = t & 1;
-        if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[pb ^ 1]), (uint32_t)CS * XCHG_BYTES);   // h_t lands here
-        if (t > 0) {
-          ok = ptx::mbar_wait(ptx::smem_u32(&h_full[pb]), ph[pb]);
-          ph[pb] ^= 1;
-          if (!ok) { atomicExch(&g_sm100_error, 12); break; }
-          ptx::fence_proxy_async();                                       // peers' st.async data -> visible to the tensor core
-        }
-        S2VT_TRACE(0);
-        if (t > 0 || have_h0) {
-          ptx::tc_fence_after();
-          // descriptors advance by constants: one 16-wide k-step = 2 core-matrix columns of h^T (2*LBO_H bytes)
-          uint64_t db = db_base[pb];
-          uint32_t ta = tmem;
-#pragma unroll 4
-          for (int ks = 0; ks < 4 * KC; ++ks) {
-            if (W_TMEM) {
-              ptx::mma_bf16_ts(tmem_acc, ta, db, idesc, ks != 0 ? 1u : 0u);
-            } else {
-              const uint64_t da = ptx::make_smem_desc(sW + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2);
-              ptx::mma_bf16_ss(tmem_acc, da, db, idesc, ks != 0 ? 1u : 0u);
-            }
-            db += (2 * LBO_H) >> 4;
-            ta += 8;
+#pragma unroll
+        for (int i = 0; i < NTL; ++i) {
+          if (!on[i]) continue;
+          const uint32_t hb = sH_all + (uint32_t)i * 2 * HBUF_BYTES;
+          if (t + 1 < T) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&h_full[i][pb ^ 1]), (uint32_t)CS * XCHG_BYTES);   // h_t lands here
+          if (t > 0) {
+            ok = ptx::mbar_wait(ptx::smem_u32(&h_full[i][pb]), ph[i][pb]);
+            ph[i][pb] ^= 1;
+            if (!ok) { atomicExch(&g_sm100_error, 12); break; }
+            ptx::fence_proxy_async();                                     // peers' st.async data -> visible to the tensor core
           }
-          ptx::mma_commit(ptx::smem_u32(&mma_done));
-          S2VT_TRACE(1);
-        } else {
-          ptx::mbar_arrive(ptx::smem_u32(&mma_done));                     // h_{-1} = 0: nothing to multiply
+          if (i == 0) S2VT_TRACE(0);
+          if (t > 0 || have_h0) {
+            ptx::tc_fence_after();
+            // descriptors advance by constants: one 16-wide k-step = 2 core-matrix columns of h^T (2*LBO_H bytes)
+            uint64_t db = ptx::make_smem_desc(hb + (uint32_t)pb * HBUF_BYTES, LBO_H, 128, 0);
+            uint32_t ta = tmem;
+            const uint32_t acc = tmem_acc0 + (uint32_t)(i * MN);
+#pragma unroll 4
+            for (int ks = 0; ks < 4 * KC; ++ks) {
+              if (W_TMEM) {
+                ptx::mma_bf16_ts(acc, ta, db, idesc, ks != 0 ? 1u : 0u);
+              } else {
+                const uint64_t da = ptx::make_smem_desc(sW + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2);
+                ptx::mma_bf16_ss(acc, da, db, idesc, ks != 0 ? 1u : 0u);
+              }
+              db += (2 * LBO_H) >> 4;
+              ta += 8;
+            }
+            ptx::mma_commit(ptx::smem_u32(&mma_done[i]));
+            if (i == 0) S2VT_TRACE(1);
+          } else {
+            ptx::mbar_arrive(ptx::smem_u32(&mma_done[i]));                // h_{-1} = 0: nothing to multiply
+          }
         }
       }
     }
-  } else {
-    // ===================== epilogue warps 0..3 =====================
-    const int g = warp;                       // phase 1: gate row block of this warp (i,f,g,o) == TMEM lane quarter
+  } else if (tile_on) {
+    // ===================== epilogue warps: tile tl, quarter wq =====================
+    const bool tr = (tl == 0) && threadIdx.x == 0;                        // trace stamps come from one thread
+    const int g = wq;                         // phase 1: gate row block of this warp (i,f,g,o) == TMEM lane quarter
     const int u = lane;                       // hidden unit within the CTA slice
     const int unit = 32 * (int)c + u;
-    const int q = warp;                       // phase 2: column group (columns 4q .. 4q+3)
+    const int q = wq;                         // phase 2: column group (columns CPT*q .. CPT*q + CPT - 1)
     float creg[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
@@ -294,29 +320,30 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
     for (int i = 0; i < PPL; ++i) {
       const uint32_t peer = (uint32_t)min(peer0 + i, CS - 1);
       peer_h[i] = ptx::mapa(sH0, peer) + chunk_off;
-      peer_bar[i] = ptx::mapa(ptx::smem_u32(&h_full[0]), peer);
+      peer_bar[i] = ptx::mapa(ptx::smem_u32(&h_full[tl][0]), peer);
     }
-    const uint32_t bar_stride = ptx::smem_u32(&h_full[1]) - ptx::smem_u32(&h_full[0]);
-    uint8_t* myPk = sPk + warp * 256;
+    const uint32_t bar_stride = ptx::smem_u32(&h_full[0][1]) - ptx::smem_u32(&h_full[0][0]);
+    uint8_t* myPk = sPk + wq * 256;
     // the stash keeps the 16-column block geometry of the BPTT kernel; a wide cluster fills half a block
     const long long stash_blk = (long long)((p.B + LSTM_NB - 1) / LSTM_NB) * CS;      // blocks per timestep
-    const int bt16 = (bt * NB) / LSTM_NB, colbase = (bt * NB) % LSTM_NB;
+    const int bt16 = b0 / LSTM_NB, colbase = b0 % LSTM_NB;
     const bool have_h0 = p.h0 != nullptr;
+    const uint32_t mma_bar = ptx::smem_u32(&mma_done[tl]);
     bool ok = true;
     for (int t = 0; t < T; ++t) {
       const int sb = t & 1;
       float* sGb = sG + sb * (4 * NB * 32);
       __nv_bfloat16* sStb = sSt + sb * (NB * 32 * 4);
       // ---- phase 1: accumulator + pre-activation -> activation -> smem
-      ok = ok && ptx::mbar_wait(ptx::smem_u32(&mma_done), (uint32_t)(t & 1));
+      ok = ok && ptx::mbar_wait(mma_bar, (uint32_t)(t & 1));
       if (!ok) { atomicExch(&g_sm100_error, 13); break; }
-      if (threadIdx.x == 0) S2VT_TRACE(2);
+      if (tr) S2VT_TRACE(2);
       float x[NB];
       if (t > 0 || have_h0) {
         ptx::tc_fence_after();
         uint32_t r[NB];
-        if constexpr (NB == 16) ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
-        else ptx::tmem_ld_32x8(tmem_acc + ((uint32_t)(warp * 32) << 16), r);
+        if constexpr (NB == 16) ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(wq * 32) << 16), r);
+        else ptx::tmem_ld_32x8(tmem_acc + ((uint32_t)(wq * 32) << 16), r);
         ptx::tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < NB; ++j) x[j] = __uint_as_float(r[j]) + pre_cur[j];
@@ -332,10 +359,10 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
         sGb[(g * NB + j) * 32 + u] = a;
         sStb[(j * 32 + u) * 4 + g] = __float2bfloat16(a);
       }
-      if (threadIdx.x == 0) S2VT_TRACE(3);
-      ptx::named_bar_sync(1, 128);
-      if (threadIdx.x == 0) S2VT_TRACE(4);
-      // ---- phase 2: cell / hidden update for (unit u, columns 4q .. 4q+3)
+      if (tr) S2VT_TRACE(3);
+      ptx::named_bar_sync(1 + tl, 128);
+      if (tr) S2VT_TRACE(4);
+      // ---- phase 2: cell / hidden update for (unit u, columns CPT*q ..)
       float hval[CPT];
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
@@ -349,7 +376,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       }
       __syncwarp();
       const uint4 hchunk = *reinterpret_cast<const uint4*>(myPk + chunk * 16);    // 8 units x 1 column, bf16
-      if (threadIdx.x == 0) S2VT_TRACE(5);
+      if (tr) S2VT_TRACE(5);
       // ---- h_t to every peer's next-step buffer (critical path first)
       if (t + 1 < T) {
         const uint32_t boff = (uint32_t)((t + 1) & 1);
@@ -357,7 +384,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
         for (int i = 0; i < PPL; ++i)
           if (peer0 + i < CS) ptx::st_async_16(peer_h[i] + boff * HBUF_BYTES, hchunk, peer_bar[i] + boff * bar_stride);
       }
-      if (threadIdx.x == 0) S2VT_TRACE(6);
+      if (tr) S2VT_TRACE(6);
       // ---- off the critical path: h_t, c_t and the gate activations to HBM
       if (lane < NCH && b0 + bcol < p.B)
         *reinterpret_cast<uint4*>(p.out + ((long long)tm(t) * p.B + b0 + bcol) * H + 32 * (int)c + 8 * m) = hchunk;
@@ -370,8 +397,9 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
       if (p.gates) {
         const uint4* ssrc = reinterpret_cast<const uint4*>(sStb);
         uint4* gdst = reinterpret_cast<uint4*>(p.gates + blk * (LSTM_NB * 32 * 4) + colbase * 32 * 4);
+        const int tid = (int)threadIdx.x - 128 * tl;
 #pragma unroll
-        for (int r = 0; r < NB / 8; ++r) gdst[threadIdx.x + 128 * r] = ssrc[threadIdx.x + 128 * r];
+        for (int r = 0; r < NB / 8; ++r) gdst[tid + 128 * r] = ssrc[tid + 128 * r];
       }
       if (t == T - 1) {
 #pragma unroll
@@ -383,7 +411,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
           }
         }
       }
-      if (threadIdx.x == 0) S2VT_TRACE(7);
+      if (tr) S2VT_TRACE(7);
     }
   }
   // no CTA may exit while peers can still write into its shared memory
@@ -394,20 +422,21 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
   if (warp == 0) ptx::tmem_dealloc(tmem, tmem_cols);
 }
 
-template <int NB, bool W_TMEM>
+template <int NB, bool W_TMEM, int NTL>
 static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFwdParams& p) {
   const int H = p.H, CS = H / 32;
-  const size_t smem_need = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + 2 * (size_t)LSTM_MN * H * 2 + 2 * (size_t)4 * NB * 32 * 4 +
-                      2 * (size_t)NB * 32 * 4 * 2 + 4 * 256;
+  const size_t tile_smem = 2 * (size_t)4 * NB * 32 * 4 + 2 * (size_t)NB * 32 * 4 * 2 + 4 * 256;
+  const size_t smem_need = 1024 + (W_TMEM ? 0 : (size_t)128 * H * 2) + (size_t)NTL * (2 * (size_t)LSTM_MN * H * 2 + tile_smem);
   // This CTA owns all of the SM's tensor memory (512 columns for H = 512): a co-resident GEMM CTA from another stream would block
   // in tcgen05.alloc until the sweep ends and would contend for the SM meanwhile.  Asking for > (227 - 97) KB keeps them out.
   const size_t smem = smem_need < (size_t)136 * 1024 ? (size_t)136 * 1024 : smem_need;
-  auto kern = lstm_fwd_cluster_kernel<NB, W_TMEM>;
+  auto kern = lstm_fwd_cluster_kernel<NB, W_TMEM, NTL>;
   S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (CS > 8) S2VT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(CS * ceil_div(p.B, NB));
-  cfg.blockDim = dim3(160);
+  const int n_clusters = ceil_div(p.B, NB * NTL);
+  cfg.gridDim = dim3(CS * n_clusters);
+  cfg.blockDim = dim3(32 * (4 * NTL + 1));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -418,7 +447,7 @@ static int launch_lstm_fwd(cudaStream_t st, const CUtensorMap& tmW, const LstmFw
   S2VT_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
   g_last_max_clusters[NB == 8 ? 0 : 1] = max_clusters;
   S2VT_REQUIRE(max_clusters >= 1, "s2vt_lstm_fwd_bf16: a cluster of %d CTAs with %zu B of shared memory cannot be scheduled on this device", CS, smem);
-  if (NB < LSTM_NB && max_clusters < ceil_div(p.B, NB)) return -1;       // the wide form must be fully co-resident; caller falls back
+  if (NB < LSTM_NB && max_clusters < n_clusters) return -1;             // the wide form must be fully co-resident; caller falls back
   S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmW, p));
   count_launch();
   return 0;
@@ -463,18 +492,20 @@ extern "C" int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_p
   if (g_dbg_flags & 8) {
     int rc = make_tmap_bf16(&tmW, w_hh_bf16, (uint64_t)H, (uint64_t)4 * H, (uint64_t)H, 64, 32);
     if (rc) return rc;
-    return launch_lstm_fwd<LSTM_NB, false>((cudaStream_t)stream, tmW, p);
+    return launch_lstm_fwd<LSTM_NB, false, 1>((cudaStream_t)stream, tmW, p);
   }
   memset(&tmW, 0, sizeof(tmW));
   // wide form (8 columns per cluster): half the DSMEM exchange and epilogue work per step, when all ceil(B/8) clusters fit at once
   if (!(g_dbg_flags & 32) && B > 8 && ceil_div(B, 8) * (H / 32) <= 128) {
-    const int rc = launch_lstm_fwd<8, true>((cudaStream_t)stream, tmW, p);
+    const int rc = launch_lstm_fwd<8, true, 1>((cudaStream_t)stream, tmW, p);
     if (rc >= 0) return rc;
   }
-  return launch_lstm_fwd<LSTM_NB, true>((cudaStream_t)stream, tmW, p);
+  if ((g_dbg_flags & 64) || g_tiles_per_cluster == 2) return launch_lstm_fwd<LSTM_NB, true, 2>((cudaStream_t)stream, tmW, p);
+  return launch_lstm_fwd<LSTM_NB, true, 1>((cudaStream_t)stream, tmW, p);
 }
 
 // debug aids (not part of the product path): per-step clock64 stamps of CTA 0 for steps [16, 48)
+extern "C" int s2vt_lstm_bf16_set_tiles_per_cluster(int n) { g_tiles_per_cluster = (n == 2) ? 2 : 1; return 0; }
 extern "C" int s2vt_debug_max_clusters(int which) { return g_last_max_clusters[which & 1]; }
 extern "C" int s2vt_debug_trace_enable(int on) { g_trace_enabled = on != 0; return 0; }
 extern "C" int s2vt_debug_set_flags(int flags) { g_dbg_flags = flags; return 0; }

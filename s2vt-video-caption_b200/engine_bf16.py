@@ -53,10 +53,21 @@ def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False, want_pla
     return dst, dst_t
 
 
-def lstm_fwd(T, B, H, n_pre, pre, bias_sum, w_bf, out, gates, cells, hT=None, cT=None, h0=None, c0=None, reverse=False):
-    with ops._timed("lstm_fwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 4 * H + 2.0 * T * B * 6 * H):
-        rc = L.load().s2vt_lstm_fwd_bf16_dir(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre), L.ptr(bias_sum), L.ptr(w_bf), L.ptr(h0),
-                                             L.ptr(c0), L.ptr(out), L.ptr(gates), L.ptr(cells), L.ptr(hT), L.ptr(cT), int(reverse))
+def lstm_fwd(T, B, H, n_pre, pre, bias_sum, w_bf, out, gates, cells, hT=None, cT=None, h0=None, c0=None, reverse=False,
+             pre_off=0, out_off=0, gates_off=0, cells_off=0, tiles_per_cluster=1):
+    """`*_off`: element offsets, to run a time range [t0, t1) of a longer sweep (chunked launches chained through h0/c0 -> hT/cT).
+    tiles_per_cluster=2: two batch tiles share a cluster's resident weights (half the SMs)."""
+    lib = L.load()
+    if tiles_per_cluster != 1:
+        lib.s2vt_lstm_bf16_set_tiles_per_cluster(tiles_per_cluster)
+    try:
+        with ops._timed("lstm_fwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 4 * H + 2.0 * T * B * 6 * H):
+            rc = lib.s2vt_lstm_fwd_bf16_dir(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre, pre_off), L.ptr(bias_sum), L.ptr(w_bf),
+                                            L.ptr(h0), L.ptr(c0), L.ptr(out, out_off), L.ptr(gates, gates_off), L.ptr(cells, cells_off),
+                                            L.ptr(hT), L.ptr(cT), int(reverse))
+    finally:
+        if tiles_per_cluster != 1:
+            lib.s2vt_lstm_bf16_set_tiles_per_cluster(1)
     L.check(rc, "s2vt_lstm_fwd_bf16")
 
 
@@ -115,6 +126,13 @@ class ShadowCache:
 _CHAIN = {}
 
 
+def _aux_stream(dev, name: str, priority: int = -1) -> torch.cuda.Stream:
+    key = (name, dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _CHAIN:
+        _CHAIN[key] = torch.cuda.Stream(device=dev, priority=priority)
+    return _CHAIN[key]
+
+
 def _chain_stream(dev) -> torch.cuda.Stream:
     """High-priority stream for the serial chain of the backward pass (dgrad product -> BPTT sweep -> dgrad product -> sweep):
     whenever a chain kernel and an off-chain kernel are both ready, the chain kernel's CTAs are placed first."""
@@ -149,6 +167,59 @@ def ce_dlogits_inplace(logits_bf, R, V, lse, targets_full, t_off, tmap, gscale):
     return logits_bf
 
 
+import os as _os
+WAVEFRONT = _os.environ.get("S2VT_WAVEFRONT", "1") != "0"      # run the two layers' sweeps side by side, a time chunk apart (False: one whole sweep after the other)
+
+
+WAVE_SPLITS = (2, 2)  # time chunks before / after step L (the embedding half of word_rnn's input starts at L: a chunk never straddles it)
+
+
+def _time_chunks(Lq: int, T: int):
+    n0, n1 = [int(x) for x in _os.environ["S2VT_WAVE_SPLITS"].split(",")] if "S2VT_WAVE_SPLITS" in _os.environ else WAVE_SPLITS
+    b = sorted(set([round(i * Lq / n0) for i in range(n0 + 1)] + [Lq + round(i * (T - Lq) / n1) for i in range(n1 + 1)]))
+    return [(b[i], b[i + 1]) for i in range(len(b) - 1)]
+
+
+def _wavefront_forward(P, S, B, Lq, H, E, T, Bp, pre1, out1, g1, c1, emb_seq, pre2, out2, g2, c2):
+    """vid_rnn and word_rnn sweeps as a wave front: the sequence is cut into time chunks; while vid_rnn runs chunk k+1 (one tile
+    per cluster, 4 clusters at B = 64), the input product of word_rnn for chunk k runs on the free SMs and word_rnn's sweep of
+    chunk k follows on 2 clusters (two tiles per cluster).  Chunks are chained through the kernels' h0/c0 -> hT/cT state, which
+    makes the result bit-identical to whole sweeps.  The serial chain shrinks from 2 x 159 steps to 159 + one chunk."""
+    dev = out1.device
+    cur = torch.cuda.current_stream(dev)
+    sg, s2 = _aux_stream(dev, "wave_gemm"), _aux_stream(dev, "wave_l2")
+    W2 = S["word_rnn.weight_ih_l0"]
+    hA, cA, hB, cB = (torch.empty(B, H, device=dev) for _ in range(4))
+    ev0 = torch.cuda.Event()
+    ev0.record(cur)
+    R = (Lq - 1) * B
+    with torch.cuda.stream(sg):                       # embedding half of word_rnn's input product: no dependence on vid_rnn at all
+        sg.wait_event(ev0)
+        gemm(R, 4 * H, E, emb_seq, E, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"], c_off=Lq * B * 4 * H, short_ctas=True)
+    ev_last = None
+    for k, (t0, t1) in enumerate(_time_chunks(Lq, T)):
+        C = t1 - t0
+        lstm_fwd(C, B, H, max(0, min(Lq, t1) - t0), pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1, hT=hA, cT=cA,
+                 h0=hA if k else None, c0=cA if k else None, pre_off=t0 * B * 4 * H if t0 < Lq else 0, out_off=t0 * B * H,
+                 gates_off=t0 * Bp * 4 * H, cells_off=t0 * Bp * H)
+        ev1 = torch.cuda.Event()
+        ev1.record(cur)
+        with torch.cuda.stream(sg):
+            sg.wait_event(ev1)
+            gemm(C * B, 4 * H, H, out1, H, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"] if t1 <= Lq else None,
+                 accumulate=t0 >= Lq, a_off=t0 * B * H, b_off=E, c_off=t0 * B * 4 * H, short_ctas=True)
+            evg = torch.cuda.Event()
+            evg.record(sg)
+        with torch.cuda.stream(s2):
+            s2.wait_event(evg)
+            lstm_fwd(C, B, H, C, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2, hT=hB, cT=cB, h0=hB if k else None,
+                     c0=cB if k else None, pre_off=t0 * B * 4 * H, out_off=t0 * B * H, gates_off=t0 * Bp * 4 * H, cells_off=t0 * Bp * H,
+                     tiles_per_cluster=2)
+            ev_last = torch.cuda.Event()
+            ev_last.record(s2)
+    cur.wait_event(ev_last)
+
+
 def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, ce=None):
     """S2VT.forward(mode='train') on tensor cores (S2VTModel.py:48-81).  Returns (fp32 logits, saved); with ce = dict(targets_full,
     t_off, tmap, loss) the vocab projection is fused with the loss and (bf16 time-major logits, saved) is returned, saved['lse']
@@ -168,20 +239,23 @@ def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, c
     out1 = torch.empty(T * B, H, dtype=BF, device=dev)
     g1 = torch.empty(T * Bp * 4 * H, dtype=BF, device=dev) if stash else None
     c1 = torch.empty(T * Bp * H, device=dev) if stash else None
-    lstm_fwd(T, B, H, Lq, pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1)
     emb_seq = torch.empty((Lq - 1) * B, E, dtype=BF, device=dev)
     rc = L.load().s2vt_embed_gather_bf16(L.stream_ptr(dev), L.ptr(S["embedding.weight"]), E, L.ptr(targets), Lq - 1, B, Lq - 1,
                                          L.ptr(emb_seq), E)
     L.check(rc, "s2vt_embed_gather_bf16")
     pre2 = torch.empty(T * B, 4 * H, device=dev)
-    gemm(T * B, 4 * H, H, out1, H, False, S["word_rnn.weight_ih_l0"], E + H, False, pre2, dense(4 * H), bias=S["b2"], b_off=E)
-    gemm((Lq - 1) * B, 4 * H, E, emb_seq, E, False, S["word_rnn.weight_ih_l0"], E + H, False, pre2, dense(4 * H), accumulate=True,
-         c_off=Lq * B * 4 * H)
     out2 = torch.empty(T * B, H, dtype=BF, device=dev)
     g2 = torch.empty(T * Bp * 4 * H, dtype=BF, device=dev) if stash else None
     c2 = torch.empty(T * Bp * H, device=dev) if stash else None
-    lstm_fwd(T, B, H, T, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2)
     R = (Lq - 1) * B
+    if WAVEFRONT and Lq >= 16 and (B + 15) // 16 + (B + 31) // 32 <= 7:
+        _wavefront_forward(P, S, B, Lq, H, E, T, Bp, pre1, out1, g1, c1, emb_seq, pre2, out2, g2, c2)
+    else:
+        lstm_fwd(T, B, H, Lq, pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1)
+        gemm(T * B, 4 * H, H, out1, H, False, S["word_rnn.weight_ih_l0"], E + H, False, pre2, dense(4 * H), bias=S["b2"], b_off=E)
+        gemm(R, 4 * H, E, emb_seq, E, False, S["word_rnn.weight_ih_l0"], E + H, False, pre2, dense(4 * H), accumulate=True,
+             c_off=Lq * B * 4 * H)
+        lstm_fwd(T, B, H, T, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2)
     lse = None
     if ce is not None:
         logits, lse = vocab_ce_fwd(R, V, H, out2, Lq * B * H, S["out_linear.weight"], P["out_linear.bias"], ce["targets_full"], ce["t_off"],

@@ -47,6 +47,7 @@ SIGNATURES = {
     "s2vt_lstm_bwd_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "s2vt_lstm_fwd_bf16_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "s2vt_lstm_bwd_bf16_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "s2vt_lstm_bf16_set_tiles_per_cluster": (_i, [_i]),
     "s2vt_lstm_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2vt_embed_gather_f32": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),
     "s2vt_embed_scatter_add_f32": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),

@@ -79,6 +79,22 @@ def test_lstm_fwd_bf16_cluster(dev, T, B, H, n_pre):
     assert (cT.double() - rcT).abs().max().item() < 2 * tol
 
 
+@pytest.mark.parametrize("T,B,H,n_pre,state", [(5, 64, 512, 5, False), (159, 64, 512, 80, False), (9, 37, 512, 0, False), (6, 48, 256, 6, True),
+                                                 (4, 16, 512, 4, True)])
+def test_lstm_fwd_bf16_two_tiles_per_cluster(dev, T, B, H, n_pre, state):
+    """Two batch tiles sharing one cluster's resident weights (half the SMs per sweep) run the same arithmetic per column:
+    every output must be bit-identical to the one-tile-per-cluster launch (ragged batches leave the second tile partly / fully idle)."""
+    lib = L.load()
+    one, _ = run_lstm_bf16(dev, T, B, H, n_pre, with_state=state, seed=7)
+    lib.s2vt_lstm_bf16_set_tiles_per_cluster(2)
+    try:
+        two, _ = run_lstm_bf16(dev, T, B, H, n_pre, with_state=state, seed=7)
+    finally:
+        lib.s2vt_lstm_bf16_set_tiles_per_cluster(1)
+    for a, b, name in zip(one, two, ("out", "gates", "cells", "hT", "cT")):
+        assert torch.equal(a, b), name
+
+
 def test_lstm_fwd_bf16_initial_state(dev):
     (out, gates, cells, hT, cT), (ro, rg, rc_, rh, rcT) = run_lstm_bf16(dev, 6, 20, 512, 6, with_state=True, seed=99)
     assert (out.double() - ro).abs().max().item() < 1e-2
@@ -114,6 +130,19 @@ def test_lstm_fwd_bf16_speed(dev):
     us_step = e0.elapsed_time(e1) * 1e3 / 10 / T
     print("\nlstm_fwd_bf16: %.3f us per timestep (B=64, H=512, T=159)" % us_step)
     assert us_step < 20.0
+    lib.s2vt_lstm_bf16_set_tiles_per_cluster(2)
+    try:
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        lib.s2vt_lstm_bf16_set_tiles_per_cluster(1)
+    print("lstm_fwd_bf16, two tiles per cluster (32 SMs): %.3f us per timestep" % (e0.elapsed_time(e1) * 1e3 / 10 / T))
 
 
 def lstm_bwd_ref(dout, gates, cells, w_hh, dout_t0):
