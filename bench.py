@@ -222,7 +222,8 @@ def main():
         f, t, m = batches[i % n_rot]
         return trainer.step(f, t, m)
 
-    for i in range(args.warmup):
+    # (with CUDA graphs: two eager steps, then one capture per rotating input buffer -- all of it before the timed region)
+    for i in range(max(args.warmup, n_rot + 2) if trainer.use_graph else args.warmup):
         step(i)
     sync_all()
     sampler = ClockSampler(local_rank)
@@ -327,7 +328,8 @@ def main():
         "config": {"workload": "BASELINE configs[1]: S2VT train step, batch %d/GPU, MSVD shape 80x4096 fp32 feats, 28-token captions "
                                "padded to 80, V=13000, H=E=512, random init" % B,
                    "global_batch": world * B, "parallelism": "dp%d" % world, "precision": precision,
-                   "l2_policy": "inputs rotate over 4 device-resident batches (336 MB > 126 MB L2)"},
+                   "l2_policy": "inputs rotate over 4 device-resident batches (336 MB > 126 MB L2)",
+                   "launch": "CUDA graph replay of the whole step (one graph per input buffer)" if trainer.use_graph and trainer._graphs else "eager"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e_value, 2), "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
         "roofline": roofline, "roofline_all": roofline_all, "kernels": kernels, "gemm_detail": gemm_detail,

@@ -126,6 +126,26 @@ int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_pre,
  * 2 = two tiles share a cluster's resident weight slice (half the SMs per sweep: lets two layers' sweeps run side by side). */
 int s2vt_lstm_bf16_set_tiles_per_cluster(int n);
 
+/* Wave-front coupling of two sweeps that run side by side on different streams, each launched ONCE (S2VT's two layers: the second
+ * sweep consumes what a GEMM makes of the first one's output, S2VTModel.py:67-77).  The sequence is cut into n_sync <= S2VT_MAX_SYNC time
+ * chunks [sync_t[k], sync_t[k+1]) (host array of n_sync + 1 ints, sync_t[0] = 0, sync_t[n_sync] = T).
+ *   signal [n_sync] u32 device counters or NULL: every (CTA, 16-column batch tile) adds 1 to signal[k] once its out / stash rows of chunk
+ *          k are visible device-wide, i.e. signal[k] reaches (H/32) * ceil(B/16) when the chunk is complete
+ *   wait   [n_sync] u32 device counters or NULL: the kernel reads `pre` rows of chunk k only once wait[k] >= wait_val (advanced by
+ *          s2vt_stream_write_value32 behind the producing GEMM); a wait of more than 2 s raises the device error flag.
+ * The caller zeroes the counters (stream-ordered) before the launches.  tiles_per_cluster as s2vt_lstm_bf16_set_tiles_per_cluster. */
+#define S2VT_MAX_SYNC 16
+int s2vt_lstm_fwd_bf16_sync(void* stream, int T, int B, int H, int n_pre,
+                            const float* pre, const float* bias_sum, const void* w_hh_bf16,
+                            const float* h0, const float* c0,
+                            void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse,
+                            int tiles_per_cluster, int n_sync, const int* sync_t, unsigned int* signal,
+                            const unsigned int* wait, unsigned int wait_val);
+/* Stream-ordered operations on such counters (cuStreamWaitValue32 with GEQ / cuStreamWriteValue32): work enqueued on `stream` after
+ * the wait starts only once *addr >= value; the write stores `value` once everything enqueued before it has completed. */
+int s2vt_stream_wait_value32(void* stream, const unsigned int* addr, unsigned int value);
+int s2vt_stream_write_value32(void* stream, unsigned int* addr, unsigned int value);
+
 /* Persistent tensor-core BPTT, the backward twin of s2vt_lstm_fwd_bf16 (same cluster shape; needs H % 128 == 0, H <= 512).
  *   dout [T,B,H] f32 (rows t < dout_t0 are zero and never read) or NULL;  gates_bf16 / cells: the forward stash (private layout)
  *   w_hh_t_bf16 [H,4H] bf16 = W_hh transposed;  dgates_bf16 [T,B,4H] bf16 out (time-major GEMM layout)
@@ -137,6 +157,25 @@ int s2vt_lstm_bwd_bf16(void* stream, int T, int B, int H, int dout_t0,
 int s2vt_lstm_bwd_bf16_dir(void* stream, int T, int B, int H, int dout_t0,
                            const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
                            void* dgates_bf16, int reverse);
+
+/* One time chunk [t0, t1) of a longer BPTT sweep (chunks are launched latest first and chained through the state gradients), so that
+ * the products consuming dgates of a chunk -- and the sweep of the layer below -- can run beside the following chunk's sweep.
+ * All buffer pointers are those of the chunk's first step (dout / dgates rows t0.., stash blocks t0..), T = t1 - t0, dout_t0 relative.
+ *   dh_in / dc_in  [B,H] f32: gradient w.r.t. h / c flowing into the chunk's last step from the chunk after it, or NULL (zero)
+ *   dh_out / dc_out [B,H] f32: the same quantities for the chunk before this one, or NULL when t0 = 0
+ *   has_prev: 1 when t0 > 0 (the stash block before `cells` holds c_{t0-1});  tiles_per_cluster: 1, or 2 = two 16-column batch tiles
+ *   share a cluster's resident weight slice (half the SMs per sweep).  Not available with reverse = 1. */
+int s2vt_lstm_bwd_bf16_chunk(void* stream, int T, int B, int H, int dout_t0,
+                             const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
+                             void* dgates_bf16, int reverse, const float* dh_in, const float* dc_in, float* dh_out, float* dc_out,
+                             int has_prev, int tiles_per_cluster);
+/* The whole sweep in one launch with the wave-front counters of s2vt_lstm_fwd_bf16_sync (chunks are walked latest first: dgates rows of
+ * chunk k are signalled, dout rows of chunk k are awaited). */
+int s2vt_lstm_bwd_bf16_sync(void* stream, int T, int B, int H, int dout_t0,
+                            const float* dout, const void* gates_bf16, const float* cells, const void* w_hh_t_bf16,
+                            void* dgates_bf16, int reverse, const float* dh_in, const float* dc_in, float* dh_out, float* dc_out,
+                            int has_prev, int tiles_per_cluster, int n_sync, const int* sync_t, unsigned int* signal,
+                            const unsigned int* wait, unsigned int wait_val);
 
 /* BPTT through one layer from a zero final-state gradient.
  *   dout   [T, B, H]  dL/dh_t from above; rows t < dout_t0 are treated as zero (and not read)
@@ -182,6 +221,12 @@ int s2vt_ce_f32(void* stream, const float* logits, int64_t R, int V, const int64
 int s2vt_adam_f32(void* stream, float* p, const float* g, float* m, float* v, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step_count, float grad_scale,
                   void* bf16_copy);
+/* The same update with the step-dependent scalars in device memory, so that a captured CUDA graph of the whole train step can be
+ * replayed: s2vt_adam_prepare does step_dev[0] += 1 and hyper_dev[0..1] = {lr_dev[0] / (1 - beta1^step), 1 / sqrt(1 - beta2^step)};
+ * s2vt_adam_f32_dev reads them.  lr lives in device memory as well (a scheduler rewrites it between replays). */
+int s2vt_adam_prepare(void* stream, int* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_dev);
+int s2vt_adam_f32_dev(void* stream, float* p, const float* g, float* m, float* v, int64_t n,
+                      float beta1, float beta2, float eps, const float* hyper_dev, float grad_scale, void* bf16_copy);
 
 /* ------------------------------------------------------------------ greedy decode, exact fp32
  * The decode loop of S2VT.forward(mode='test'), S2VTModel.py:88-110.

@@ -1,5 +1,11 @@
 """s2vt-video-caption_b200: B200-native (sm_100a) drop-in for the S2VT encoder-decoder hot path of
 Kamino666/S2VT-video-caption.  Import through the `s2vt_b200` shim at the repo root."""
+import os as _os
+
+# the wave-front schedule keeps several streams busy at once (two sweeps, the products between them, weight gradients, NCCL): give each
+# its own hardware queue so that a stream memory wait never holds up an unrelated stream (read by the driver at context creation)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .att_model import ATT_PARAM_ORDER, Att_Baseline
 from .criterion import MaskCriterion
 from .data import DeviceFeatureStore, ids_to_sentence, predictions_to_dict

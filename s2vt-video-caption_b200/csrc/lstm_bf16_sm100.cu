@@ -98,6 +98,12 @@ struct LstmFwdParams {
   long long* trace;                // debug: [TRACE_STEPS][8] clock64 stamps of CTA 0, or null
   int dbg_flags;
   int reverse;                     // 1: processing step s reads / writes time index T-1-s (the reverse direction of a bidirectional LSTM)
+  // wave-front coupling of two sweeps that run side by side, each launched once (never with reverse):
+  int n_sync;                      // time chunks: chunk k = steps [sync_t[k], sync_t[k+1])
+  int sync_t[S2VT_MAX_SYNC + 1];
+  unsigned int* signal;            // [n_sync] counters, += 1 per (CTA, batch tile) once its out / stash rows of chunk k are visible, or null
+  const unsigned int* wait;        // [n_sync] counters advanced by the producer of `pre`: chunk k is read once wait[k] >= wait_val, or null
+  unsigned int wait_val;
 };
 constexpr int TRACE_STEPS = 32, TRACE_T0 = 16;
 __device__ long long g_lstm_trace[TRACE_STEPS * 8];
@@ -140,7 +146,7 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int tl = warp < CTRL ? (warp >> 2) : 0;                           // batch tile served by this epilogue warp
+  const int tl = (NTL > 1 && warp < CTRL) ? (warp >> 2) : 0;                           // batch tile served by this epilogue warp
   const int wq = warp & 3;                                                // its TMEM lane quarter / gate / column group
   const uint32_t c = ptx::cluster_ctarank();                              // hidden-unit slice of this CTA
   const int bt = blockIdx.x / CS;                                         // cluster index
@@ -299,16 +305,26 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
         const float* src = pre_row0 + t * step_stride;
         if (row_stride != 0) {
 #pragma unroll
-          for (int j = 0; j < NB; ++j) dst[j] = __ldg(src + j * row_stride);
+          for (int j = 0; j < NB; ++j) dst[j] = __ldcg(src + j * row_stride);   // (L2: a chunk of pre may be produced while this kernel runs)
         } else {                                                        // ...unless it exists (slow path, partial tile only)
 #pragma unroll
-          for (int j = 0; j < NB; ++j) dst[j] = __ldg(src + (long long)(min(b0 + j, p.B - 1) - min(b0, p.B - 1)) * 4 * H);
+          for (int j = 0; j < NB; ++j) dst[j] = __ldcg(src + (long long)(min(b0 + j, p.B - 1) - min(b0, p.B - 1)) * 4 * H);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < NB; ++j) dst[j] = bias_g;
       }
     };
+    // wave-front coupling: wk / sk = next chunk to wait for / to signal
+    int wk = 0, sk = 0;
+    bool ok = true;
+    auto wait_chunk = [&](int s) {                                        // before the first read of pre at step s
+      if (p.wait && wk < p.n_sync && s == p.sync_t[wk]) {
+        if (!ptx::wait_counter_geq(p.wait + wk, p.wait_val)) { atomicExch(&g_sm100_error, 14); ok = false; }
+        ++wk;
+      }
+    };
+    wait_chunk(0);
     load_pre(0, pre_cur);
     // st.async targets: this lane serves h chunk (m = octet of units, colL = column within the warp's CPT) to PPL peers
     const int chunk = lane & (NCH - 1), colL = chunk >> 2, m = chunk & 3;
@@ -329,7 +345,6 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
     const int bt16 = b0 / LSTM_NB, colbase = b0 % LSTM_NB;
     const bool have_h0 = p.h0 != nullptr;
     const uint32_t mma_bar = ptx::smem_u32(&mma_done[tl]);
-    bool ok = true;
     for (int t = 0; t < T; ++t) {
       const int sb = t & 1;
       float* sGb = sG + sb * (4 * NB * 32);
@@ -352,7 +367,10 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
 #pragma unroll
         for (int j = 0; j < NB; ++j) x[j] = pre_cur[j];
       }
-      if (t + 1 < T) load_pre(t + 1, pre_cur);                            // prefetch: latency hides behind the rest of the step
+      if (t + 1 < T) {
+        wait_chunk(t + 1);
+        load_pre(t + 1, pre_cur);                                         // prefetch: latency hides behind the rest of the step
+      }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const float a = fmaf(sc, ptx::fast_tanh(sc * x[j]), sh);
@@ -411,8 +429,16 @@ lstm_fwd_cluster_kernel(const __grid_constant__ CUtensorMap tmW, const LstmFwdPa
           }
         }
       }
+      if (p.signal && sk < p.n_sync && t + 1 == p.sync_t[sk + 1]) {       // chunk complete: publish it to the consumer of out
+        __threadfence();
+        ptx::named_bar_sync(1 + tl, 128);
+        if ((int)threadIdx.x == 128 * tl) ptx::red_release_gpu_add(p.signal + sk, 1u);
+        ++sk;
+      }
       if (tr) S2VT_TRACE(7);
     }
+    if (p.signal && (int)threadIdx.x == 128 * tl)                         // (error exit: never leave a consumer waiting)
+      for (; sk < p.n_sync; ++sk) ptx::red_release_gpu_add(p.signal + sk, 1u);
   }
   // no CTA may exit while peers can still write into its shared memory
   ptx::tc_fence_before();
@@ -470,7 +496,20 @@ extern "C" int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_p
                                       const float* pre, const float* bias_sum, const void* w_hh_bf16,
                                       const float* h0, const float* c0,
                                       void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse) {
+  return s2vt_lstm_fwd_bf16_sync(stream, T, B, H, n_pre, pre, bias_sum, w_hh_bf16, h0, c0, out_bf16, gates_bf16, cells, hT, cT, reverse,
+                                 g_tiles_per_cluster, 0, nullptr, nullptr, nullptr, 0);
+}
+
+extern "C" int s2vt_lstm_fwd_bf16_sync(void* stream, int T, int B, int H, int n_pre,
+                                       const float* pre, const float* bias_sum, const void* w_hh_bf16,
+                                       const float* h0, const float* c0,
+                                       void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse,
+                                       int tiles_per_cluster, int n_sync, const int* sync_t, unsigned int* signal,
+                                       const unsigned int* wait, unsigned int wait_val) {
   S2VT_REQUIRE(T >= 1 && B >= 1, "s2vt_lstm_fwd_bf16: bad dims");
+  S2VT_REQUIRE(n_sync >= 0 && n_sync <= S2VT_MAX_SYNC, "s2vt_lstm_fwd_bf16_sync: at most %d chunks", S2VT_MAX_SYNC);
+  S2VT_REQUIRE(n_sync == 0 || (sync_t && (signal || wait) && !reverse), "s2vt_lstm_fwd_bf16_sync: chunks need sync_t and a counter array, and the forward direction");
+  S2VT_REQUIRE(tiles_per_cluster == 1 || tiles_per_cluster == 2, "s2vt_lstm_fwd_bf16_sync: tiles_per_cluster must be 1 or 2");
   S2VT_REQUIRE(H % 64 == 0 && H >= 64 && H <= 512, "s2vt_lstm_fwd_bf16: the cluster-resident kernel needs H %% 64 == 0 and 64 <= H <= 512 (got %d)", H);
   S2VT_REQUIRE(bias_sum && w_hh_bf16 && out_bf16, "s2vt_lstm_fwd_bf16: null pointer");
   S2VT_REQUIRE(n_pre <= 0 || pre, "s2vt_lstm_fwd_bf16: pre is null but n_pre > 0");
@@ -483,6 +522,12 @@ extern "C" int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_p
   p.trace = nullptr;
   p.dbg_flags = g_dbg_flags;
   p.reverse = reverse ? 1 : 0;
+  p.n_sync = n_sync; p.signal = n_sync ? signal : nullptr; p.wait = n_sync ? wait : nullptr; p.wait_val = wait_val;
+  for (int i = 0; i <= n_sync && n_sync > 0; ++i) {
+    S2VT_REQUIRE(sync_t[i] >= 0 && sync_t[i] <= T && (i == 0 || sync_t[i] > sync_t[i - 1]), "s2vt_lstm_fwd_bf16_sync: sync_t must increase from 0 to T");
+    p.sync_t[i] = sync_t[i];
+  }
+  S2VT_REQUIRE(n_sync == 0 || (p.sync_t[0] == 0 && p.sync_t[n_sync] == T), "s2vt_lstm_fwd_bf16_sync: sync_t must start at 0 and end at T");
   if (g_trace_enabled) {
     void* sym = nullptr;
     S2VT_CHECK_CUDA(cudaGetSymbolAddress(&sym, g_lstm_trace));
@@ -496,11 +541,11 @@ extern "C" int s2vt_lstm_fwd_bf16_dir(void* stream, int T, int B, int H, int n_p
   }
   memset(&tmW, 0, sizeof(tmW));
   // wide form (8 columns per cluster): half the DSMEM exchange and epilogue work per step, when all ceil(B/8) clusters fit at once
-  if (!(g_dbg_flags & 32) && B > 8 && ceil_div(B, 8) * (H / 32) <= 128) {
+  if (!(g_dbg_flags & 32) && B > 8 && ceil_div(B, 8) * (H / 32) <= 128 && n_sync == 0 && tiles_per_cluster == 1) {
     const int rc = launch_lstm_fwd<8, true, 1>((cudaStream_t)stream, tmW, p);
     if (rc >= 0) return rc;
   }
-  if ((g_dbg_flags & 64) || g_tiles_per_cluster == 2) return launch_lstm_fwd<LSTM_NB, true, 2>((cudaStream_t)stream, tmW, p);
+  if ((g_dbg_flags & 64) || tiles_per_cluster == 2) return launch_lstm_fwd<LSTM_NB, true, 2>((cudaStream_t)stream, tmW, p);
   return launch_lstm_fwd<LSTM_NB, true, 1>((cudaStream_t)stream, tmW, p);
 }
 

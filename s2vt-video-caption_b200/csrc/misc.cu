@@ -138,9 +138,19 @@ __global__ void mean_kernel(const float* __restrict__ x, long long n, float* __r
 }
 
 // ---------------------------------------------------------------- Adam
+// step <- step + 1 and this step's bias-corrected scalars, all on the device: a captured CUDA graph replays it with no host value baked in
+__global__ void adam_prepare_kernel(int* __restrict__ step, const float* __restrict__ lr, float beta1, float beta2, float* __restrict__ hyper) {
+  const int t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t), bc2 = 1.0 - pow((double)beta2, (double)t);
+  hyper[0] = (float)((double)*lr / bc1);
+  hyper[1] = (float)(1.0 / sqrt(bc2));
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float beta1, float beta2, float eps, float step_size, float inv_bc2_sqrt,
-                            float grad_scale, __nv_bfloat16* __restrict__ shadow) {
+                            float grad_scale, __nv_bfloat16* __restrict__ shadow, const float* __restrict__ hyper) {
+  if (hyper) { step_size = hyper[0]; inv_bc2_sqrt = hyper[1]; }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
@@ -196,6 +206,7 @@ using namespace s2vt;
 extern "C" int s2vt_abi_version(void) { return S2VT_ABI_VERSION; }
 extern "C" const char* s2vt_last_error(void) { return err_buf(); }
 extern "C" int64_t s2vt_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int64_t s2vt_add_launch_count(int64_t n) { count_launch((int)n); return (int64_t)g_launches.load(); }
 
 extern "C" int s2vt_embed_gather_f32(void* stream, const float* table, int E, const int64_t* ids, int64_t ids_ld,
                                      int B, int n_t, float* out, int64_t out_ld) {
@@ -263,7 +274,26 @@ extern "C" int s2vt_adam_f32(void* stream, float* p, const float* g, float* m, f
   int blocks = ceil_div(n, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt, grad_scale,
-                                                        (__nv_bfloat16*)bf16_copy);
+                                                        (__nv_bfloat16*)bf16_copy, nullptr);
+  S2VT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int s2vt_adam_prepare(void* stream, int* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_dev) {
+  S2VT_REQUIRE(step_dev && lr_dev && hyper_dev, "s2vt_adam_prepare: null pointer");
+  adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_dev, beta1, beta2, hyper_dev);
+  S2VT_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int s2vt_adam_f32_dev(void* stream, float* p, const float* g, float* m, float* v, int64_t n,
+                                 float beta1, float beta2, float eps, const float* hyper_dev, float grad_scale, void* bf16_copy) {
+  S2VT_REQUIRE(p && g && m && v && hyper_dev, "s2vt_adam_f32_dev: null pointer");
+  if (n == 0) return 0;
+  int blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, 0.f, grad_scale, (__nv_bfloat16*)bf16_copy,
+                                                        hyper_dev);
   S2VT_CHECK_LAUNCH();
   return 0;
 }

@@ -61,6 +61,29 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ cross-kernel counters in global memory (wave-front coupling)
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *p >= target (a counter another kernel / a stream memory operation advances); false after 2 s
+__device__ __forceinline__ bool wait_counter_geq(const unsigned int* p, uint32_t target) {
+  if ((int32_t)(ld_acquire_gpu(p) - target) >= 0) return true;
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int spin = 0; spin < 16; ++spin) {
+      if ((int32_t)(ld_acquire_gpu(p) - target) >= 0) return true;
+      __nanosleep(64);
+    }
+    if (globaltimer_ns() - t0 > 2000000000ull) return false;
+  }
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

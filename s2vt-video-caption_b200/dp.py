@@ -9,6 +9,7 @@ Bucket order = order in which backward finishes them: out_linear -> word_rnn -> 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -96,7 +97,7 @@ class DataParallelTrainer:
     """model + FusedAdam + gradient all-reduce: `step(feats, targets)` is the reference's train-loop body
     (train.py:116-127) on this rank's shard."""
 
-    def __init__(self, model, optimizer, group=None, overlap: bool = True):
+    def __init__(self, model, optimizer, group=None, overlap: bool = True, cuda_graph: Optional[bool] = None):
         self.model, self.opt = model, optimizer
         f = optimizer._ensure_flat()
         names = [n for n, _ in model.named_parameters()]
@@ -106,6 +107,17 @@ class DataParallelTrainer:
         # Adam per bucket, right behind that bucket's all-reduce: needs gradients that backward writes in place (CUDA path)
         self.early_adam = f["g"].is_cuda
         optimizer.attach(model, on_bucket_ready=self._bucket_ready)
+        # The step is ~70 kernel launches on 6 streams; enqueueing them from Python takes longer than the GPU needs to run them.
+        # After two eager steps (kernel code loaded, caches warm) the whole step -- forward, backward, all-reduce, Adam -- is captured
+        # into a CUDA graph per distinct (feats, targets) buffer pair and replayed; nothing step-dependent is baked into it
+        # (Adam's step count / lr live on the device).  S2VT_CUDA_GRAPH=0 or cuda_graph=False keeps every step eager.
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("S2VT_CUDA_GRAPH", "1") != "0"
+        self.use_graph = bool(cuda_graph) and f["g"].is_cuda
+        self._graphs: Dict[tuple, tuple] = {}
+        self._eager_steps = 0
+        self._pool = None
+        self.max_graphs = 8
 
     def _bucket_ready(self, bucket: str) -> None:
         """Called by backward once every kernel producing `bucket`'s gradients has been enqueued (and nothing later in the step
@@ -121,7 +133,7 @@ class DataParallelTrainer:
         else:
             self.opt.step_range(a, b)
 
-    def step(self, feats, targets, mask=None):
+    def _step_eager(self, feats, targets, mask=None):
         self.opt.zero_grad(set_to_none=True)
         loss = self.model.forward_loss(feats, targets, mask)
         self.opt.begin_step()
@@ -129,3 +141,41 @@ class DataParallelTrainer:
         self.reducer.finish()
         self.opt.finish_step()
         return loss
+
+    def step(self, feats, targets, mask=None):
+        from . import ops
+        if not (self.use_graph and feats.is_cuda and self.model._use_bf16()) or ops._PROFILE is not None:
+            self._eager_steps += 1
+            return self._step_eager(feats, targets, mask)
+        key = (feats.data_ptr(), targets.data_ptr(), tuple(feats.shape), tuple(targets.shape), feats.requires_grad)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if self._eager_steps < 2 or len(self._graphs) >= self.max_graphs:
+                self._eager_steps += 1
+                return self._step_eager(feats, targets, mask)
+            ent = self._capture(key, feats, targets, mask)
+        graph, loss, n_launch, _keep = ent
+        self.opt.sync_lr()
+        graph.replay()
+        self.opt.note_replayed_step()
+        from .lib import load
+        load().s2vt_add_launch_count(n_launch)
+        return loss
+
+    def _capture(self, key, feats, targets, mask):
+        from .lib import launch_count
+        f = self.opt._flat
+        host_step, epoch = f["step"], None
+        self.opt.sync_lr()
+        torch.cuda.synchronize(feats.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = launch_count()
+        with torch.cuda.graph(graph, pool=self._pool):
+            loss = self._step_eager(feats, targets, mask)
+        n_launch = launch_count() - n0
+        if self._pool is None:
+            self._pool = graph.pool()
+        f["step"] = host_step                    # capturing enqueued nothing: the step happens at replay
+        ent = (graph, loss, n_launch, (feats, targets))
+        self._graphs[key] = ent
+        return ent

@@ -7,6 +7,8 @@ train_backward_f32 (the exact path) -- operands are bf16 instead of fp32.
 """
 from __future__ import annotations
 
+import ctypes
+import os as _os
 from typing import Dict, Optional
 
 import torch
@@ -53,28 +55,36 @@ def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False, want_pla
     return dst, dst_t
 
 
+def _sync_args(sync):
+    """sync = (bounds, signal, wait, wait_val): chunk boundaries [0, ..., T] and the u32 counter rows (tensors or None)."""
+    if sync is None:
+        return 0, None, None, None, 0
+    bounds, signal, wait, wait_val = sync
+    arr = (ctypes.c_int * len(bounds))(*bounds)
+    return len(bounds) - 1, arr, L.ptr(signal), L.ptr(wait), int(wait_val)
+
+
 def lstm_fwd(T, B, H, n_pre, pre, bias_sum, w_bf, out, gates, cells, hT=None, cT=None, h0=None, c0=None, reverse=False,
-             pre_off=0, out_off=0, gates_off=0, cells_off=0, tiles_per_cluster=1):
+             pre_off=0, out_off=0, gates_off=0, cells_off=0, tiles_per_cluster=1, sync=None):
     """`*_off`: element offsets, to run a time range [t0, t1) of a longer sweep (chunked launches chained through h0/c0 -> hT/cT).
-    tiles_per_cluster=2: two batch tiles share a cluster's resident weights (half the SMs)."""
-    lib = L.load()
-    if tiles_per_cluster != 1:
-        lib.s2vt_lstm_bf16_set_tiles_per_cluster(tiles_per_cluster)
-    try:
-        with ops._timed("lstm_fwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 4 * H + 2.0 * T * B * 6 * H):
-            rc = lib.s2vt_lstm_fwd_bf16_dir(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre, pre_off), L.ptr(bias_sum), L.ptr(w_bf),
-                                            L.ptr(h0), L.ptr(c0), L.ptr(out, out_off), L.ptr(gates, gates_off), L.ptr(cells, cells_off),
-                                            L.ptr(hT), L.ptr(cT), int(reverse))
-    finally:
-        if tiles_per_cluster != 1:
-            lib.s2vt_lstm_bf16_set_tiles_per_cluster(1)
+    tiles_per_cluster=2: two batch tiles share a cluster's resident weights (half the SMs).  sync: wave-front counters (_sync_args)."""
+    n_sync, sync_t, signal, wait, wait_val = _sync_args(sync)
+    with ops._timed("lstm_fwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 4 * H + 2.0 * T * B * 6 * H):
+        rc = L.load().s2vt_lstm_fwd_bf16_sync(L.stream_ptr(out.device), T, B, H, n_pre, L.ptr(pre, pre_off), L.ptr(bias_sum), L.ptr(w_bf),
+                                              L.ptr(h0), L.ptr(c0), L.ptr(out, out_off), L.ptr(gates, gates_off), L.ptr(cells, cells_off),
+                                              L.ptr(hT), L.ptr(cT), int(reverse), tiles_per_cluster, n_sync, sync_t, signal, wait, wait_val)
     L.check(rc, "s2vt_lstm_fwd_bf16")
 
 
-def lstm_bwd(T, B, H, dout_t0, dout, gates, cells, w_t_bf, dgates, reverse=False):
+def lstm_bwd(T, B, H, dout_t0, dout, gates, cells, w_t_bf, dgates, reverse=False, dout_off=0, gates_off=0, cells_off=0, dgates_off=0,
+             dh_in=None, dc_in=None, dh_out=None, dc_out=None, has_prev=False, tiles_per_cluster=1, sync=None):
+    """`*_off` (elements) + the state gradients run one time chunk of a longer sweep; sync: wave-front counters (_sync_args)."""
+    n_sync, sync_t, signal, wait, wait_val = _sync_args(sync)
     with ops._timed("lstm_bwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 3 * H + 2.0 * T * B * 8 * H):
-        rc = L.load().s2vt_lstm_bwd_bf16_dir(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
-                                             L.ptr(w_t_bf), L.ptr(dgates), int(reverse))
+        rc = L.load().s2vt_lstm_bwd_bf16_sync(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout, dout_off), L.ptr(gates, gates_off),
+                                              L.ptr(cells, cells_off), L.ptr(w_t_bf), L.ptr(dgates, dgates_off), int(reverse), L.ptr(dh_in),
+                                              L.ptr(dc_in), L.ptr(dh_out), L.ptr(dc_out), int(has_prev), tiles_per_cluster, n_sync, sync_t,
+                                              signal, wait, wait_val)
     L.check(rc, "s2vt_lstm_bwd_bf16")
 
 
@@ -167,57 +177,148 @@ def ce_dlogits_inplace(logits_bf, R, V, lse, targets_full, t_off, tmap, gscale):
     return logits_bf
 
 
-import os as _os
-WAVEFRONT = _os.environ.get("S2VT_WAVEFRONT", "1") != "0"      # run the two layers' sweeps side by side, a time chunk apart (False: one whole sweep after the other)
+WAVEFRONT = _os.environ.get("S2VT_WAVEFRONT", "1") != "0"       # run the two layers' sweeps side by side, a time chunk apart (False: one whole sweep after the other)
 
 
-WAVE_SPLITS = (2, 2)  # time chunks before / after step L (the embedding half of word_rnn's input starts at L: a chunk never straddles it)
+WAVE_SPLITS = (3, 3)  # time chunks before / after step L (the embedding half of word_rnn's input starts at L: a chunk never straddles it)
 
 
-def _time_chunks(Lq: int, T: int):
+def _time_bounds(Lq: int, T: int):
     n0, n1 = [int(x) for x in _os.environ["S2VT_WAVE_SPLITS"].split(",")] if "S2VT_WAVE_SPLITS" in _os.environ else WAVE_SPLITS
-    b = sorted(set([round(i * Lq / n0) for i in range(n0 + 1)] + [Lq + round(i * (T - Lq) / n1) for i in range(n1 + 1)]))
-    return [(b[i], b[i + 1]) for i in range(len(b) - 1)]
+    return sorted(set([round(i * Lq / n0) for i in range(n0 + 1)] + [Lq + round(i * (T - Lq) / n1) for i in range(n1 + 1)]))
+
+
+def _wave_tiles(which: str):
+    """(tiles per cluster of the leading sweep, of the trailing sweep).  Two tiles per cluster halve a sweep's SMs (32 instead of 64 at
+    B = 64) at 1.2-1.3x its step time; the trailing sweep must use 2 for both sweeps to be co-resident (at most 7 clusters of 16 fit)."""
+    a, b = [int(x) for x in _os.environ.get("S2VT_%s_TILES" % which, "1,2").split(",")]
+    return a, b
+
+
+_COUNTERS = {}
+
+
+def _wave_counters(dev) -> torch.Tensor:
+    """[4, 16] u32 (as int32) device counters: rows = forward signal / ready, backward signal / ready (s2vt_lstm_fwd_bf16_sync)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _COUNTERS:
+        _COUNTERS[key] = torch.zeros(4, 16, dtype=torch.int32, device=dev)
+    return _COUNTERS[key]
+
+
+def wave_ok(B: int, Lq: int) -> bool:
+    return WAVEFRONT and Lq >= 16 and (B + 15) // 16 + (B + 31) // 32 <= 7
 
 
 def _wavefront_forward(P, S, B, Lq, H, E, T, Bp, pre1, out1, g1, c1, emb_seq, pre2, out2, g2, c2):
-    """vid_rnn and word_rnn sweeps as a wave front: the sequence is cut into time chunks; while vid_rnn runs chunk k+1 (one tile
-    per cluster, 4 clusters at B = 64), the input product of word_rnn for chunk k runs on the free SMs and word_rnn's sweep of
-    chunk k follows on 2 clusters (two tiles per cluster).  Chunks are chained through the kernels' h0/c0 -> hT/cT state, which
-    makes the result bit-identical to whole sweeps.  The serial chain shrinks from 2 x 159 steps to 159 + one chunk."""
+    """vid_rnn and word_rnn sweeps as a wave front, each sweep ONE launch (its clusters are placed once, on an empty machine, and the
+    weights enter tensor memory once).  The sequence is cut into time chunks: vid_rnn's kernel counts a chunk's finished (CTA, tile)
+    pairs in a device counter; the input product of word_rnn for that chunk waits for the count on a side stream (stream memory
+    operation, no SM is held), runs on the free SMs and raises the chunk's ready flag, which word_rnn's kernel -- resident from the
+    start on its own clusters -- polls before it reads the chunk's pre-activations.  The arithmetic is that of two whole sweeps, so
+    the result is bit-identical; the serial chain shrinks from 2 x 159 steps to 159 + one chunk."""
     dev = out1.device
+    lib = L.load()
     cur = torch.cuda.current_stream(dev)
     sg, s2 = _aux_stream(dev, "wave_gemm"), _aux_stream(dev, "wave_l2")
     W2 = S["word_rnn.weight_ih_l0"]
-    hA, cA, hB, cB = (torch.empty(B, H, device=dev) for _ in range(4))
+    ctr = _wave_counters(dev)
+    ctr[0:2].zero_()
+    bounds = _time_bounds(Lq, T)
+    n_arrive = (H // 32) * ((B + 15) // 16)
+    ntl_lead, ntl_trail = _wave_tiles("FWD")
     ev0 = torch.cuda.Event()
     ev0.record(cur)
     R = (Lq - 1) * B
-    with torch.cuda.stream(sg):                       # embedding half of word_rnn's input product: no dependence on vid_rnn at all
-        sg.wait_event(ev0)
-        gemm(R, 4 * H, E, emb_seq, E, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"], c_off=Lq * B * 4 * H, short_ctas=True)
-    ev_last = None
-    for k, (t0, t1) in enumerate(_time_chunks(Lq, T)):
-        C = t1 - t0
-        lstm_fwd(C, B, H, max(0, min(Lq, t1) - t0), pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1, hT=hA, cT=cA,
-                 h0=hA if k else None, c0=cA if k else None, pre_off=t0 * B * 4 * H if t0 < Lq else 0, out_off=t0 * B * H,
-                 gates_off=t0 * Bp * 4 * H, cells_off=t0 * Bp * H)
-        ev1 = torch.cuda.Event()
-        ev1.record(cur)
-        with torch.cuda.stream(sg):
-            sg.wait_event(ev1)
-            gemm(C * B, 4 * H, H, out1, H, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"] if t1 <= Lq else None,
-                 accumulate=t0 >= Lq, a_off=t0 * B * H, b_off=E, c_off=t0 * B * 4 * H, short_ctas=True)
-            evg = torch.cuda.Event()
-            evg.record(sg)
+    lstm_fwd(T, B, H, Lq, pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1, tiles_per_cluster=ntl_lead, sync=(bounds, ctr[0], None, 0))
+    ev_g = torch.cuda.Event()
+
+    def trailing_sweep(after_products: bool):
         with torch.cuda.stream(s2):
-            s2.wait_event(evg)
-            lstm_fwd(C, B, H, C, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2, hT=hB, cT=cB, h0=hB if k else None,
-                     c0=cB if k else None, pre_off=t0 * B * 4 * H, out_off=t0 * B * H, gates_off=t0 * Bp * 4 * H, cells_off=t0 * Bp * H,
-                     tiles_per_cluster=2)
-            ev_last = torch.cuda.Event()
-            ev_last.record(s2)
-    cur.wait_event(ev_last)
+            s2.wait_event(ev_g if after_products else ev0)
+            lstm_fwd(T, B, H, T, pre2, S["b2"], S["word_rnn.weight_hh_l0"], out2, g2, c2, tiles_per_cluster=ntl_trail,
+                     sync=(bounds, None, ctr[1], 1))
+
+    def products():
+        with torch.cuda.stream(sg):
+            sg.wait_event(ev0)
+            # embedding half of word_rnn's input product: no dependence on vid_rnn at all
+            gemm(R, 4 * H, E, emb_seq, E, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"], c_off=Lq * B * 4 * H, short_ctas=True)
+            for k in range(len(bounds) - 1):
+                t0, t1 = bounds[k], bounds[k + 1]
+                L.check(lib.s2vt_stream_wait_value32(sg.cuda_stream, L.ptr(ctr, k), n_arrive), "s2vt_stream_wait_value32")
+                gemm((t1 - t0) * B, 4 * H, H, out1, H, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"] if t1 <= Lq else None,
+                     accumulate=t0 >= Lq, a_off=t0 * B * H, b_off=E, c_off=t0 * B * 4 * H, short_ctas=True)
+                L.check(lib.s2vt_stream_write_value32(sg.cuda_stream, L.ptr(ctr, 16 + k), 1), "s2vt_stream_write_value32")
+            ev_g.record(sg)
+
+    _run_coupled(("fwd", dev.index, B, Lq, H, E), trailing_sweep, products)
+    cur.wait_stream(s2)
+    cur.wait_event(ev_g)
+
+
+_WARM = set()
+
+
+def _run_coupled(key, trailing_sweep, products):
+    """Enqueue a trailing sweep (which spins on device flags) and the products that raise those flags.  Normally the sweep goes first, so
+    that it is resident before its first chunk is ready.  The first time a configuration runs, the products go first and the sweep
+    starts behind them: the CUDA runtime loads a kernel's code on its first launch and may have to wait for the device to drain to do
+    so -- with a spinning kernel resident that would never happen.  (S2VT_WAVEFRONT=safe keeps this order: profilers that serialise
+    kernels need it.)"""
+    if key in _WARM and _os.environ.get("S2VT_WAVEFRONT") != "safe":
+        trailing_sweep(False)
+        products()
+    else:
+        products()
+        trailing_sweep(True)
+        _WARM.add(key)
+
+
+def _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, events):
+    """The two BPTT sweeps as a wave front, the mirror image of _wavefront_forward: word_rnn's sweep (one launch) counts finished chunks,
+    latest first; the product giving dL/d(vid_rnn output) for a chunk waits for the count on a side stream, runs on free SMs and raises
+    the ready flag that vid_rnn's sweep (one launch, own clusters) polls.  `events` = (dout2 ready, dg2 complete, dout1 complete,
+    dg1 complete); on return the chain stream has joined everything."""
+    B, Lq, F, H, E, V, T = saved["dims"]
+    dev = dl_bf.device
+    lib = L.load()
+    R = (Lq - 1) * B
+    ev_dout2, ev_dg2, ev_dout1, ev_dg1 = events
+    sg, s1 = _aux_stream(dev, "wave_bgemm"), _aux_stream(dev, "wave_bl1")
+    ntl_lead, ntl_trail = _wave_tiles("BWD")
+    bounds = _time_bounds(Lq, T)
+    n_arrive = (H // 32) * ((B + 15) // 16)
+    W2 = S["word_rnn.weight_ih_l0"]
+    with torch.cuda.stream(chain):
+        ctr = _wave_counters(dev)
+        ctr[2:4].zero_()
+        gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=Lq * B * H)
+        ev_dout2.record(chain)
+        lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2, tiles_per_cluster=ntl_lead,
+                 sync=(bounds, ctr[2], None, 0))
+        ev_dg2.record(chain)
+    def trailing_sweep(after_products: bool):
+        with torch.cuda.stream(s1):
+            s1.wait_event(ev_dout1 if after_products else ev_dout2)
+            lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1, tiles_per_cluster=ntl_trail,
+                     sync=(bounds, None, ctr[3], 1))
+            ev_dg1.record(s1)
+
+    def products():
+        with torch.cuda.stream(sg):
+            sg.wait_event(ev_dout2)
+            for k in range(len(bounds) - 2, -1, -1):
+                t0, t1 = bounds[k], bounds[k + 1]
+                L.check(lib.s2vt_stream_wait_value32(sg.cuda_stream, L.ptr(ctr, 32 + k), n_arrive), "s2vt_stream_wait_value32")
+                gemm((t1 - t0) * B, H, 4 * H, dg2, 4 * H, False, W2, E + H, True, dout1, dense(H), a_off=t0 * B * 4 * H, b_off=E,
+                     c_off=t0 * B * H, short_ctas=True)
+                L.check(lib.s2vt_stream_write_value32(sg.cuda_stream, L.ptr(ctr, 48 + k), 1), "s2vt_stream_write_value32")
+            ev_dout1.record(sg)
+
+    _run_coupled(("bwd", dev.index, B, Lq, H, E), trailing_sweep, products)
+    chain.wait_event(ev_dg1)
+    chain.wait_event(ev_dout1)
 
 
 def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, ce=None):
@@ -248,7 +349,7 @@ def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, c
     g2 = torch.empty(T * Bp * 4 * H, dtype=BF, device=dev) if stash else None
     c2 = torch.empty(T * Bp * H, device=dev) if stash else None
     R = (Lq - 1) * B
-    if WAVEFRONT and Lq >= 16 and (B + 15) // 16 + (B + 31) // 32 <= 7:
+    if wave_ok(B, Lq):
         _wavefront_forward(P, S, B, Lq, H, E, T, Bp, pre1, out1, g1, c1, emb_seq, pre2, out2, g2, c2)
     else:
         lstm_fwd(T, B, H, Lq, pre1, S["b1"], S["vid_rnn.weight_hh_l0"], out1, g1, c1)
@@ -302,15 +403,18 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     dout1 = torch.empty(T * B, H, device=dev)
     dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
     ev_dout2, ev_dg2, ev_dout1, ev_dg1 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-    with torch.cuda.stream(chain):
-        gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
-        ev_dout2.record(chain)
-        lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
-        ev_dg2.record(chain)
-        gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
-        ev_dout1.record(chain)
-        lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
-        ev_dg1.record(chain)
+    if wave_ok(B, Lq):
+        _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, (ev_dout2, ev_dg2, ev_dout1, ev_dg1))
+    else:
+        with torch.cuda.stream(chain):
+            gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
+            ev_dout2.record(chain)
+            lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
+            ev_dg2.record(chain)
+            gemm(T * B, H, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, dout1, dense(H), b_off=E)
+            ev_dout1.record(chain)
+            lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
+            ev_dg1.record(chain)
     # ---- out_linear:  dW = dl^T h,  db = colsum(dl)   (beside the word_rnn sweep; released together with it)
     cur.wait_event(ev_dout2)
     gW = _new("out_linear.weight", V, H)

@@ -27,13 +27,16 @@ def dense(ld: int) -> RowMap:
     return RowMap(1, int(ld), 0)
 
 
-_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vp, _i, _i64, _f, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 
 # name -> (restype, argtypes); kept in one table so tests can compare it with the header
 SIGNATURES = {
     "s2vt_abi_version": (_i, []),
     "s2vt_last_error": (C.c_char_p, []),
     "s2vt_launch_count": (_i64, []),
+    "s2vt_add_launch_count": (_i64, [_i64]),
+    "s2vt_adam_prepare": (_i, [_vp, _vp, _vp, _f, _f, _vp]),
+    "s2vt_adam_f32_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _vp, _f, _vp]),
     "s2vt_has_tcgen05": (_i, []),
     "s2vt_device_error_flag": (_i, [_vp]),
     "s2vt_gemm_f32": (_i, [_vp, _i, _i, _i, _vp, RowMap, _i, _vp, RowMap, _i, _vp, RowMap, _vp, _i, _i, _i64]),
@@ -48,6 +51,11 @@ SIGNATURES = {
     "s2vt_lstm_fwd_bf16_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "s2vt_lstm_bwd_bf16_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "s2vt_lstm_bf16_set_tiles_per_cluster": (_i, [_i]),
+    "s2vt_lstm_fwd_bf16_sync": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _u32]),
+    "s2vt_lstm_bwd_bf16_sync": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _u32]),
+    "s2vt_stream_wait_value32": (_i, [_vp, _vp, _u32]),
+    "s2vt_stream_write_value32": (_i, [_vp, _vp, _u32]),
+    "s2vt_lstm_bwd_bf16_chunk": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i]),
     "s2vt_lstm_bwd_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2vt_embed_gather_f32": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),
     "s2vt_embed_scatter_add_f32": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),

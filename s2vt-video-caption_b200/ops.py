@@ -165,6 +165,23 @@ def adam_f32(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor,
     L.check(rc, "s2vt_adam_f32")
 
 
+def adam_prepare(step_dev: torch.Tensor, lr_dev: torch.Tensor, beta1: float, beta2: float, hyper_dev: torch.Tensor) -> None:
+    rc = L.load().s2vt_adam_prepare(L.stream_ptr(step_dev.device), L.ptr(step_dev), L.ptr(lr_dev), beta1, beta2, L.ptr(hyper_dev))
+    L.check(rc, "s2vt_adam_prepare")
+
+
+def adam_f32_dev(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, beta1: float, beta2: float, eps: float,
+                 hyper_dev: torch.Tensor, grad_scale: float = 1.0, bf16_copy: Optional[torch.Tensor] = None) -> None:
+    """adam_f32 with this step's scalars read from device memory (adam_prepare): replayable inside a CUDA graph."""
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+    L.require_cuda(p, g, m, v, hyper_dev)
+    with _timed("adam_f32", 0.0, 28.0 * p.numel()):
+        rc = L.load().s2vt_adam_f32_dev(L.stream_ptr(p.device), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), beta1, beta2, eps,
+                                        L.ptr(hyper_dev), grad_scale, L.ptr(bf16_copy))
+    L.check(rc, "s2vt_adam_f32_dev")
+
+
 def greedy_decode_f32(B: int, H: int, E: int, V: int, n_steps: int, sos_ix: int, pre2_vid: torch.Tensor, pre_off: int,
                       w_cat: torch.Tensor, emb: torch.Tensor, w_out: torch.Tensor, b_out: torch.Tensor, h2: torch.Tensor,
                       c2: torch.Tensor, tokens: torch.Tensor) -> None:

@@ -48,6 +48,11 @@ class FusedAdam(torch.optim.Optimizer):
         # bf16 shadow of the weights, refreshed by the Adam kernel itself (the tensor-core path reads weights as bf16)
         shadow = torch.zeros(n, dtype=torch.bfloat16, device=dev)
         self._flat = dict(params=ps, offsets=offsets, p=flat, g=g, m=m, v=v2, step=step, n=n, shadow=shadow, shadow_state=None)
+        if dev.type == "cuda":
+            # the step counter, lr and this step's bias-corrected scalars also live on the device (ops.adam_prepare): nothing that
+            # changes from step to step is a kernel argument, so a captured CUDA graph of the train step can be replayed
+            self._flat.update(step_dev=torch.tensor([step], dtype=torch.int32, device=dev), lr_host=None,
+                              lr_dev=torch.zeros(1, device=dev), hyper_dev=torch.zeros(2, device=dev))
         return self._flat
 
     def flat_grad_views(self):
@@ -83,19 +88,43 @@ class FusedAdam(torch.optim.Optimizer):
 
     # ---- bucket-wise stepping: Adam on a slice of the flat buffer as soon as that slice's gradient is final, so that most of
     # the (HBM-bound) update runs beside the BPTT sweeps instead of after them.  begin_step() / step_range()* / finish_step().
+    def sync_lr(self) -> None:
+        """Copies the group's learning rate to the device when it changed (a scheduler wrote it); stream-ordered, outside any graph."""
+        f = self._ensure_flat()
+        lr = float(self.param_groups[0]["lr"])
+        if "lr_dev" in f and f["lr_host"] != lr:
+            f["lr_dev"].fill_(lr)
+            f["lr_host"] = lr
+
     @torch.no_grad()
     def begin_step(self) -> None:
         f = self._ensure_flat()
         f["step"] += 1
         f["stepped"] = []
+        if "step_dev" in f:
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_lr()
+            group = self.param_groups[0]
+            ops.adam_prepare(f["step_dev"], f["lr_dev"], float(group["betas"][0]), float(group["betas"][1]), f["hyper_dev"])
+
+    def note_replayed_step(self) -> None:
+        """Host-side bookkeeping for one replay of a captured train step (the device did begin_step .. finish_step itself)."""
+        f = self._flat
+        f["step"] += 1
+        ops.WEIGHT_EPOCH += 1
+        f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))
 
     @torch.no_grad()
     def step_range(self, a: int, b: int, grad_scale: float = 1.0) -> None:
         """Adam on flat elements [a, b) (a multiple of 8) with this step's bias correction; launches on the current stream."""
         f = self._flat
         group = self.param_groups[0]
-        ops.adam_f32(f["p"][a:b], f["g"][a:b], f["m"][a:b], f["v"][a:b], float(group["lr"]), float(group["betas"][0]),
-                     float(group["betas"][1]), float(group["eps"]), f["step"], grad_scale=grad_scale, bf16_copy=f["shadow"][a:b])
+        if "step_dev" in f:
+            ops.adam_f32_dev(f["p"][a:b], f["g"][a:b], f["m"][a:b], f["v"][a:b], float(group["betas"][0]), float(group["betas"][1]),
+                             float(group["eps"]), f["hyper_dev"], grad_scale=grad_scale, bf16_copy=f["shadow"][a:b])
+        else:
+            ops.adam_f32(f["p"][a:b], f["g"][a:b], f["m"][a:b], f["v"][a:b], float(group["lr"]), float(group["betas"][0]),
+                         float(group["betas"][1]), float(group["eps"]), f["step"], grad_scale=grad_scale, bf16_copy=f["shadow"][a:b])
         f["stepped"].append((a, b))
 
     @torch.no_grad()
@@ -125,6 +154,8 @@ class FusedAdam(torch.optim.Optimizer):
                 gv.copy_(p.grad)
         group = self.param_groups[0]
         f["step"] += 1
+        if "step_dev" in f:
+            f["step_dev"].fill_(f["step"])          # (the bucket-wise path counts on the device; keep both in step)
         ops.adam_f32(f["p"], f["g"], f["m"], f["v"], float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
                      float(group["eps"]), f["step"], grad_scale=grad_scale, bf16_copy=f["shadow"])
         f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))

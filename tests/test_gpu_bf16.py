@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 import s2vt_b200  # noqa: E402
 from s2vt_b200 import lib as L  # noqa: E402
+from s2vt_b200 import engine_bf16 as EB  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -197,6 +198,54 @@ def test_lstm_bwd_bf16_cluster(dev, T, B, H, dout_t0):
     assert err < (1e-2 + 1e-3 * T) * scale, (err, scale)
 
 
+def _bwd_inputs(dev, T, B, H, seed):
+    g = torch.Generator().manual_seed(seed)
+    lib = L.load()
+    Bp = int(lib.s2vt_lstm_bf16_batch_pad(B))
+    nbt, CS = Bp // 16, H // 32
+    w = ((torch.rand(4 * H, H, generator=g) * 2 - 1) / H ** 0.5).to(dev).bfloat16()
+    gates = torch.rand(T, Bp, 4 * H, generator=g).to(dev)
+    gates[:, :, 2 * H:3 * H] = gates[:, :, 2 * H:3 * H] * 2 - 1
+    gates = gates.bfloat16()
+    cells = torch.randn(T, Bp, H, generator=g).to(dev)
+    dout = (torch.randn(T, B, H, generator=g) * 0.1).to(dev)
+    gates_p = gates.view(T, nbt, 16, 4, CS, 32).permute(0, 1, 4, 2, 5, 3).contiguous()
+    cells_p = cells.view(T, nbt, 16, CS, 32).permute(0, 1, 3, 2, 4).contiguous()
+    return w.T.contiguous(), gates_p, cells_p, dout, Bp
+
+
+@pytest.mark.parametrize("T,B,H,dout_t0,cuts,ntl", [(12, 64, 512, 0, (5,), 1), (12, 64, 512, 0, (), 2), (159, 64, 512, 80, (40, 80, 120), 1),
+                                                     (159, 64, 512, 80, (40, 80, 120), 2), (9, 37, 256, 3, (1, 8), 2), (7, 16, 128, 0, (3,), 2),
+                                                     (6, 48, 512, 0, (2, 4), 2)])
+def test_lstm_bwd_bf16_chunks_and_tiles(dev, T, B, H, dout_t0, cuts, ntl):
+    """A sweep cut into time chunks (latest first, chained through dh / dc) and / or run with two batch tiles per cluster gives the
+    whole-sweep result: identical bits for the tile variant, fp32-reassociation noise (the carried dh is summed in another order)
+    for the chunked one."""
+    lib = L.load()
+    wt, gates_p, cells_p, dout, Bp = _bwd_inputs(dev, T, B, H, seed=T + B + H)
+    whole = torch.full((T, B, 4 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+    L.check(lib.s2vt_lstm_bwd_bf16(L.stream_ptr(dev), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates_p), L.ptr(cells_p), L.ptr(wt), L.ptr(whole)), "bwd")
+    got = torch.full((T, B, 4 * H), float("nan"), device=dev, dtype=torch.bfloat16)
+    bounds = [0] + list(cuts) + [T]
+    dh, dc = None, None
+    for k in range(len(bounds) - 2, -1, -1):
+        t0, t1 = bounds[k], bounds[k + 1]
+        dh_o = torch.full((B, H), float("nan"), device=dev) if t0 > 0 else None
+        dc_o = torch.full((B, H), float("nan"), device=dev) if t0 > 0 else None
+        EB.lstm_bwd(t1 - t0, B, H, max(0, dout_t0 - t0), dout, gates_p, cells_p, wt, got, dout_off=t0 * B * H, gates_off=t0 * Bp * 4 * H,
+                    cells_off=t0 * Bp * H, dgates_off=t0 * B * 4 * H, dh_in=dh, dc_in=dc, dh_out=dh_o, dc_out=dc_o, has_prev=t0 > 0,
+                    tiles_per_cluster=ntl)
+        dh, dc = dh_o, dc_o
+    assert lib.s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+    assert torch.isfinite(got.float()).all()
+    if not cuts:
+        assert torch.equal(got, whole)
+    else:
+        scale = whole.float().abs().max().item()
+        assert (got.float() - whole.float()).abs().max().item() <= 2e-2 * scale
+        assert (got.float() - whole.float()).abs().mean().item() <= 1e-3 * scale
+
+
 def test_lstm_bwd_bf16_speed(dev):
     T, B, H = 159, 64, 512
     g = torch.Generator().manual_seed(2)
@@ -221,6 +270,83 @@ def test_lstm_bwd_bf16_speed(dev):
     us_step = e0.elapsed_time(e1) * 1e3 / 10 / T
     print("\nlstm_bwd_bf16: %.3f us per timestep (B=64, H=512, T=159)" % us_step)
     assert us_step < 20.0
+
+    def run2():
+        L.check(lib.s2vt_lstm_bwd_bf16_chunk(L.stream_ptr(dev), T, B, H, 0, L.ptr(dout), L.ptr(gates), L.ptr(cells), L.ptr(wt), L.ptr(dg), 0,
+                                             None, None, None, None, 0, 2), "bwd")
+    for _ in range(3):
+        run2()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        run2()
+    e1.record()
+    torch.cuda.synchronize()
+    print("lstm_bwd_bf16, two tiles per cluster (32 SMs): %.3f us per timestep" % (e0.elapsed_time(e1) * 1e3 / 10 / T))
+
+
+def test_wavefront_matches_sequential_sweeps(dev):
+    """The wave front (two single-launch sweeps coupled through device counters, chunked input products between them) computes what
+    the sequential order computes: forward quantities are bit-identical (same kernels, same operands); gradients below the coupling
+    product differ only by the summation order of its K-split."""
+    torch.manual_seed(5)
+    V, F, H, E, Lq, B = 1000, 256, 512, 512, 80, 64
+    model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    feats = torch.randn(B, Lq, F, device=dev)
+    targets = torch.randint(0, V, (B, Lq), device=dev)
+    assert EB.wave_ok(B, Lq)
+    res = {}
+    old = EB.WAVEFRONT
+    try:
+        for mode in (True, False, True):
+            EB.WAVEFRONT = mode
+            model.zero_grad(set_to_none=True)
+            loss = model.forward_loss(feats, targets)
+            loss.backward()
+            torch.cuda.synchronize()
+            assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+            res[mode] = (loss.item(), {k: p.grad.clone() for k, p in model.named_parameters()})
+    finally:
+        EB.WAVEFRONT = old
+    assert abs(res[True][0] - res[False][0]) <= 1e-6 * abs(res[False][0])
+    for k in res[True][1]:
+        a, b = res[True][1][k].double(), res[False][1][k].double()
+        # not bit-identical: word_rnn's pre-activations are summed in another order (embedding half first), and bf16 roundings of
+        # activations / dgates flip on 1e-7 differences
+        assert (a - b).norm().item() <= 1e-2 * b.norm().item(), k
+
+
+def test_cuda_graph_step_matches_eager(dev):
+    """DataParallelTrainer replays a captured CUDA graph of the whole step from its third step on: weights after 5 steps must equal
+    those of an all-eager trainer (same kernels in the same order; Adam's step count and lr live on the device), and an lr change
+    between replays must take effect."""
+    from s2vt_b200.dp import DataParallelTrainer
+    V, F, H, E, Lq, B = 1000, 256, 512, 512, 80, 64
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn(B, Lq, F, generator=g).to(dev)
+    targets = torch.randint(0, V, (B, Lq), generator=g).to(dev)
+    out = {}
+    for graph in (False, True):
+        torch.manual_seed(3)
+        model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+        opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-3)
+        tr = DataParallelTrainer(model, opt, cuda_graph=graph)
+        losses = []
+        for i in range(6):
+            if i == 4:
+                opt.param_groups[0]["lr"] = 5e-4
+            losses.append(float(tr.step(feats, targets).item()))
+        torch.cuda.synchronize()
+        assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+        assert bool(tr._graphs) == graph
+        out[graph] = (losses, {k: p.detach().clone() for k, p in model.named_parameters()}, opt._flat["step"], int(opt._flat["step_dev"].item()))
+    assert out[True][2] == out[False][2] == 6 and out[True][3] == out[False][3] == 6
+    for a, b in zip(out[True][0], out[False][0]):
+        assert abs(a - b) <= 1e-4 * abs(b), (out[True][0], out[False][0])
+    assert out[False][0][-1] < out[False][0][0]
+    for k in out[True][1]:
+        a, b = out[True][1][k].double(), out[False][1][k].double()
+        assert (a - b).norm().item() <= 1e-3 * b.norm().item(), k
 
 
 # ------------------------------------------------------------------ whole train step on tensor cores vs the reference goldens

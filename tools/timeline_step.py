@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Timeline of one train step of the bench workload: start / end of every C-ABI call (CUDA events on the launching stream,
+relative to the step's first call), plus host enqueue time per step against device time per step.
+
+    python tools/timeline_step.py [--batch 64] > gpurun_out/timeline.txt
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import s2vt_b200  # noqa: E402
+from s2vt_b200 import ops  # noqa: E402
+from s2vt_b200.dp import DataParallelTrainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=10)
+    args = ap.parse_args()
+    C = bench.CFG
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = s2vt_b200.S2VT(C["V"], C["F"], C["L"], dim_hid=C["H"], dim_embed=C["E"], train_precision="bf16").to(dev)
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-4)
+    trainer = DataParallelTrainer(model, opt)
+    batches = [bench.synth_batch(args.batch, 1234 + i, device=dev) for i in range(4)]
+    for i in range(5):
+        trainer.step(*batches[i % 4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        trainer.step(*batches[i % 4])
+    t_enq = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    print("host enqueue %.3f ms/step, wall incl. device %.3f ms/step" % (1e3 * t_enq / args.steps, 1e3 * t_all / args.steps))
+    print("device error flag:", s2vt_b200.load().s2vt_device_error_flag(None))
+    with ops.profile() as prof:
+        trainer.step(*batches[0])
+        torch.cuda.synchronize()
+    recs = prof.records
+    first = recs[0][1]
+    rows = []
+    for tag, e0, e1, flops, nbytes in recs:
+        rows.append((first.elapsed_time(e0) * 1e3, first.elapsed_time(e1) * 1e3, tag))
+    end = max(r[1] for r in rows)
+    print("step span %.1f us (instrumented)" % end)
+    for a, b, tag in rows:
+        print("%9.1f %9.1f %8.1f  %s" % (a, b, b - a, tag))
+
+
+if __name__ == "__main__":
+    main()
