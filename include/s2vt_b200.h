@@ -134,17 +134,53 @@ int s2vt_lstm_bf16_set_tiles_per_cluster(int n);
  *   wait   [n_sync] u32 device counters or NULL: the kernel reads `pre` rows of chunk k only once wait[k] >= wait_val (advanced by
  *          s2vt_stream_write_value32 behind the producing GEMM); a wait of more than 2 s raises the device error flag.
  * The caller zeroes the counters (stream-ordered) before the launches.  tiles_per_cluster as s2vt_lstm_bf16_set_tiles_per_cluster. */
-#define S2VT_MAX_SYNC 16
+#define S2VT_MAX_SYNC 64
 int s2vt_lstm_fwd_bf16_sync(void* stream, int T, int B, int H, int n_pre,
                             const float* pre, const float* bias_sum, const void* w_hh_bf16,
                             const float* h0, const float* c0,
                             void* out_bf16, void* gates_bf16, float* cells, float* hT, float* cT, int reverse,
                             int tiles_per_cluster, int n_sync, const int* sync_t, unsigned int* signal,
                             const unsigned int* wait, unsigned int wait_val);
+/* The product that couples two such sweeps, as ONE launch resident beside them:  C[M,N] (f32, dense) (+)= A[M,K] * B (+ bias), with A's
+ * rows produced chunk by chunk by the first sweep and C's rows consumed chunk by chunk by the second.  Persistent tcgen05 kernel on at
+ * most max_ctas SMs; its scheduler hands out 128-row tiles in row order (reverse_m = 1: from the last row block to the first, for a
+ * sweep that walks backwards in time) and, before a tile's TMA loads, waits until wait[k] >= wait_val for every chunk k the tile
+ * overlaps (chunk k = rows [sync_row[k], sync_row[k+1]), sync_row[0] = 0, sync_row[n_sync] = M; wait[] = the first sweep's `signal`
+ * counters).  When the last tile overlapping chunk k has landed in C (and is visible device-wide) ready[k] is incremented: the second
+ * sweep waits for ready[k] >= 1.  done [n_sync] = scratch counters; the caller zeroes done and ready (stream-ordered) beforehand.
+ * A is K-major ([M, lda]); B is K-major ([N, ldb], b_mn_major = 0) or MN-major ([K, ldb], b_mn_major = 1).  accumulate = 1: C += (TMA
+ * reduce-add, no bias).  Because the kernel sits on its SMs from the start, the coupling never waits for CTA slots behind the bulk
+ * products that run beside the sweeps (CTAs are dispatched in launch order whatever the stream priorities: tools/probe_priority.py).
+ * Replaces the per-chunk `input2 @ W_ih` slices of S2VTModel.py:75-77 and their autograd transposes. */
+int s2vt_gemm_bf16_gated(void* stream, int M, int N, int K, const void* A_bf16, int64_t lda, const void* B_bf16, int64_t ldb,
+                         int b_mn_major, float* C, int64_t ldc, const float* bias, int accumulate, int max_ctas, int reverse_m,
+                         int n_sync, const int* sync_row, const unsigned int* wait, unsigned int wait_val,
+                         unsigned int* done, unsigned int* ready);
 /* Stream-ordered operations on such counters (cuStreamWaitValue32 with GEQ / cuStreamWriteValue32): work enqueued on `stream` after
  * the wait starts only once *addr >= value; the write stores `value` once everything enqueued before it has completed. */
 int s2vt_stream_wait_value32(void* stream, const unsigned int* addr, unsigned int value);
 int s2vt_stream_write_value32(void* stream, unsigned int* addr, unsigned int value);
+/* high = 1: the calling thread's following s2vt_gemm_bf16 launches of the one-tile-per-CTA kernel carry the device's greatest priority as a
+ * launch attribute (kept by a captured graph's kernel node), so that their CTAs take SM slots ahead of queued CTAs of bulk products
+ * running beside a sweep.  high = 0 restores the default. */
+int s2vt_set_launch_priority(int high);
+/* n > 0: the calling thread's following launches of the memory-bound bulk kernels (s2vt_adam_f32*, s2vt_colsum_bf16) use at most n CTAs
+ * (grid-stride).  For work that runs beside a recurrence sweep: CTAs are dispatched in launch order, so a kernel with more CTAs than
+ * free SM slots keeps every later kernel -- the wave front's coupling products -- waiting until its last CTA has been placed; a capped
+ * kernel is resident at once and leaves slots over.  0 restores full-machine grids.  (The GEMM counterpart is s2vt_gemm_bf16_set_mode.) */
+int s2vt_set_bulk_cta_cap(int n);
+/* Executable graphs that honour per-node priorities.  `graph` is a cudaGraph_t (e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()).
+ * Stream capture records each kernel node's priority (that of its stream, or its launch attribute), but cudaGraphInstantiate ignores
+ * them unless cudaGraphInstantiateFlagUseNodePriority is given -- which s2vt_graph_instantiate(use_node_priority = 1) does.  The caller
+ * keeps `graph` (and the memory its nodes reference) alive for as long as the executable graph is launched.
+ * s2vt_graph_kernel_priorities: writes the priority of up to max_nodes kernel nodes (node order) and the number of kernel nodes to *n_out. */
+int s2vt_graph_instantiate(void* graph, int use_node_priority, void** exec_out);
+int s2vt_graph_launch(void* exec, void* stream);
+int s2vt_graph_exec_destroy(void* exec);
+int s2vt_graph_kernel_priorities(void* graph, int* prio_out, int max_nodes, int* n_out);
+/* Measurement aid: a one-thread kernel that stores %globaltimer (ns) into *slot in stream order.  Unlike CUDA events it can be captured
+ * into a graph, so tools/timeline_step.py gets the device-side timeline of a REPLAYED step. */
+int s2vt_timestamp(void* stream, unsigned long long* slot);
 
 /* Persistent tensor-core BPTT, the backward twin of s2vt_lstm_fwd_bf16 (same cluster shape; needs H % 128 == 0, H <= 512).
  *   dout [T,B,H] f32 (rows t < dout_t0 are zero and never read) or NULL;  gates_bf16 / cells: the forward stash (private layout)

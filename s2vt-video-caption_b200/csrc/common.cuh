@@ -49,4 +49,6 @@ __device__ __forceinline__ float sigmoidf_exact(float x) { return 1.0f / (1.0f +
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+int bulk_cta_cap();          // s2vt_set_bulk_cta_cap of the calling thread (0 = none); defined in misc.cu
+
 }  // namespace s2vt

@@ -42,7 +42,22 @@ struct GemmPersistParams {
   float* ce_ztgt;                   // [M]
   const int64_t* ce_targets;
   RowMap ce_tmap;
+  // wave-front gating (s2vt_gemm_bf16_gated): the rows of A are produced chunk by chunk by a recurrence sweep running beside this
+  // kernel, and the rows of C are consumed chunk by chunk by a second sweep.  Chunk k = rows [sync_row[k], sync_row[k+1]).
+  int n_sync, reverse_m, tiles_m;
+  int sync_row[S2VT_MAX_SYNC + 1];
+  int sync_expect[S2VT_MAX_SYNC];   // epilogue-warp completions after which chunk k of C is whole (4 x the units overlapping it)
+  const unsigned int* sync_wait;    // [n_sync] a unit reads A only once sync_wait[k] >= sync_wait_val for every chunk it overlaps
+  unsigned int sync_wait_val;
+  unsigned int* sync_done;          // [n_sync] completion counters (zeroed by the caller)
+  unsigned int* sync_ready;         // [n_sync] += 1 when chunk k of C is whole and visible device-wide
 };
+
+// first row of the unit's tile: tiles are walked from the last row block to the first when the producing sweep runs backwards in time
+__device__ __forceinline__ int unit_m0(const GemmPersistParams& p, int tile) {
+  const int mt = tile / p.tiles_n;
+  return (p.reverse_m ? p.tiles_m - 1 - mt : mt) * PBM;
+}
 
 namespace ptx {
 __device__ __forceinline__ void p_tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
@@ -115,9 +130,16 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         ++ri;
         if (unit < 0) break;
         const int split = unit / p.tiles, tile = unit % p.tiles;
-        const int n0 = (tile % p.tiles_n) * PBN, m0 = (tile / p.tiles_n) * PBM;
+        const int n0 = (tile % p.tiles_n) * PBN, m0 = unit_m0(p, tile);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         bool ok = true;
+        if (p.n_sync) {                                              // the sweep beside us has published these rows of A?
+          const int m1 = min(p.M, m0 + PBM);
+          for (int k = 0; k < p.n_sync && ok; ++k)
+            if (p.sync_row[k] < m1 && p.sync_row[k + 1] > m0) ok = ptx::wait_counter_geq(p.sync_wait + k, p.sync_wait_val);
+          if (!ok) { atomicExch(&g_sm100_error, 38); break; }
+          asm volatile("fence.proxy.async;" ::: "memory");          // acquire (generic proxy) before the TMA reads (async proxy)
+        }
         for (int kb = kb0; kb < kb1 && ok; ++kb, ++it) {
           const int s = it % PSTAGES;
           ok = ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ((it / PSTAGES) & 1) ^ 1);
@@ -194,7 +216,7 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       ++ri;
       if (unit < 0) break;
       const int split = unit / p.tiles, tile = unit % p.tiles;
-      const int n0 = (tile % p.tiles_n) * PBN, m0 = (tile / p.tiles_n) * PBM;
+      const int n0 = (tile % p.tiles_n) * PBN, m0 = unit_m0(p, tile);
       const uint32_t a = ai & 1;
       // bias of the tile's 256 columns, spread over the lanes (lane l holds columns 32k + l); fetched before the accumulator wait,
       // handed to every row with shuffles: a load inside the chunk loop would put an L2 round trip on each chunk's critical path
@@ -325,6 +347,23 @@ gemm_bf16_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         if (p.ce_part && my_m < p.M) p.ce_part[(long long)my_m * p.tiles_n + (tile % p.tiles_n)] = make_float2(ce_m, ce_s);
       }
+      if (p.n_sync) {                                              // publish: this warp's 32 x 256 block of C has landed
+        if (lane == 0) {
+          ptx::p_bulk_wait0();
+          asm volatile("fence.proxy.async;" ::: "memory");        // async-proxy writes before the generic-proxy release below
+          __threadfence();
+          const int m1 = min(p.M, m0 + PBM);
+          for (int k = 0; k < p.n_sync; ++k) {
+            if (p.sync_row[k] < m1 && p.sync_row[k + 1] > m0) {
+              if (atomicAdd(p.sync_done + k, 1u) == (unsigned)p.sync_expect[k] - 1u) {
+                __threadfence();
+                ptx::red_release_gpu_add(p.sync_ready + k, 1u);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
     if (lane == 0) ptx::p_bulk_wait0();                            // all stores of this warp have landed before the CTA retires
   }
@@ -345,16 +384,25 @@ static thread_local int g_max_ctas = 0;      // 0 = all SMs
 static int g_num_sms = 0;
 
 // Returns 0 on success, < 0 when this kernel does not cover the case (caller falls back), > 0 on error.
+struct GemmGate {                    // s2vt_gemm_bf16_gated
+  int n_sync, reverse_m, max_ctas;
+  const int* sync_row;
+  const unsigned int* wait;
+  unsigned int wait_val;
+  unsigned int *done, *ready;
+};
+
 int launch_gemm_persist_ce(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
                            void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate,
-                           float2* ce_part, float* ce_ztgt, const int64_t* ce_targets, RowMap ce_tmap) {
+                           float2* ce_part, float* ce_ztgt, const int64_t* ce_targets, RowMap ce_tmap, const GemmGate* gate = nullptr) {
   if (out_bf16 && accumulate) return -1;
   if (!g_num_sms) {
     int dev = 0;
     S2VT_CHECK_CUDA(cudaGetDevice(&dev));
     S2VT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int G = g_max_ctas > 0 ? (g_max_ctas < g_num_sms ? g_max_ctas : g_num_sms) : g_num_sms;
+  const int want_ctas = gate ? gate->max_ctas : g_max_ctas;
+  const int G = want_ctas > 0 ? (want_ctas < g_num_sms ? want_ctas : g_num_sms) : g_num_sms;
   CUtensorMap tmA, tmB, tmC;
   int rc;
   rc = a_mn ? make_tmap_any(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64, 2)
@@ -368,12 +416,26 @@ int launch_gemm_persist_ce(cudaStream_t st, int M, int N, int K, const void* A, 
   GemmPersistParams p{};
   p.M = M; p.N = N; p.K = K; p.num_kb = (K + PBK - 1) / PBK;
   p.tiles_n = ceil_div(N, PBN);
-  p.tiles = p.tiles_n * ceil_div(M, PBM);
+  p.tiles_m = ceil_div(M, PBM);
+  p.tiles = p.tiles_n * p.tiles_m;
   p.out_bf16 = out_bf16; p.bias = bias;
+  if (gate && gate->n_sync > 0) {
+    p.n_sync = gate->n_sync; p.reverse_m = gate->reverse_m;
+    p.sync_wait = gate->wait; p.sync_wait_val = gate->wait_val; p.sync_done = gate->done; p.sync_ready = gate->ready;
+    for (int k = 0; k <= gate->n_sync; ++k) p.sync_row[k] = gate->sync_row[k];
+    for (int k = 0; k < gate->n_sync; ++k) {
+      int tiles_over = 0;
+      for (int mt = 0; mt < p.tiles_m; ++mt) {
+        const int m0 = mt * PBM, m1 = M < m0 + PBM ? M : m0 + PBM;
+        if (p.sync_row[k] < m1 && p.sync_row[k + 1] > m0) ++tiles_over;
+      }
+      p.sync_expect[k] = 4 * tiles_over * p.tiles_n;
+    }
+  }
   p.ce_part = ce_part; p.ce_ztgt = ce_ztgt; p.ce_targets = ce_targets; p.ce_tmap = ce_tmap;
   // split K so that the unit count fills whole rounds of the G resident CTAs (fp32 outputs only: partials are summed in L2 by TMA)
   int best = 1;
-  if (!out_bf16) {
+  if (!out_bf16 && !(gate && gate->n_sync > 0)) {                 // (a gated product publishes whole tiles: no K slices)
     double best_score = -1.0;
     for (int s = 1; s <= 16; ++s) {
       if (s > 1 && p.num_kb / s < 8) break;
@@ -417,6 +479,11 @@ int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int
 }
 
 void gemm_persist_set_max_ctas(int n) { g_max_ctas = n; }
+
+int launch_gemm_persist_gated(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, int b_mn,
+                              void* C, int64_t ldc, const float* bias, int accumulate, const GemmGate& gate) {
+  return launch_gemm_persist_ce(st, M, N, K, A, lda, 0, B, ldb, b_mn, C, ldc, 0, bias, accumulate, nullptr, nullptr, nullptr, RowMap{1, 1, 0}, &gate);
+}
 
 // one warp per row: merge the per-tile (max, sum-exp) partials -> log-sum-exp; row loss = lse - z[target]
 __global__ void ce_combine_kernel(const float2* __restrict__ part, int tiles_n, const float* __restrict__ ztgt, long long R,
@@ -519,6 +586,24 @@ extern "C" int s2vt_vocab_ce_fwd_bf16(void* stream, int R, int V, int K, const v
     S2VT_CHECK_LAUNCH();
   }
   return 0;
+}
+
+extern "C" int s2vt_gemm_bf16_gated(void* stream, int M, int N, int K, const void* A_bf16, int64_t lda, const void* B_bf16, int64_t ldb,
+                                    int b_mn_major, float* C, int64_t ldc, const float* bias, int accumulate, int max_ctas, int reverse_m,
+                                    int n_sync, const int* sync_row, const unsigned int* wait, unsigned int wait_val,
+                                    unsigned int* done, unsigned int* ready) {
+  S2VT_REQUIRE(M > 0 && N > 0 && K > 0, "s2vt_gemm_bf16_gated: dimensions must be positive (M=%d N=%d K=%d)", M, N, K);
+  S2VT_REQUIRE(A_bf16 && B_bf16 && C, "s2vt_gemm_bf16_gated: null operand");
+  S2VT_REQUIRE(n_sync >= 1 && n_sync <= S2VT_MAX_SYNC && sync_row && wait && done && ready,
+               "s2vt_gemm_bf16_gated: needs 1..%d chunks with their row bounds and counters", S2VT_MAX_SYNC);
+  S2VT_REQUIRE(sync_row[0] == 0 && sync_row[n_sync] == M, "s2vt_gemm_bf16_gated: sync_row must run from 0 to M");
+  for (int k = 0; k < n_sync; ++k) S2VT_REQUIRE(sync_row[k + 1] > sync_row[k], "s2vt_gemm_bf16_gated: sync_row must increase");
+  S2VT_REQUIRE(aligned16(C) && ldc % 4 == 0 && ldc >= N, "s2vt_gemm_bf16_gated: C must be dense, 16-byte aligned rows");
+  S2VT_REQUIRE(max_ctas >= 1, "s2vt_gemm_bf16_gated: max_ctas must be >= 1");
+  GemmGate gate{n_sync, reverse_m ? 1 : 0, max_ctas, sync_row, wait, wait_val, done, ready};
+  const int rc = launch_gemm_persist_gated((cudaStream_t)stream, M, N, K, A_bf16, lda, B_bf16, ldb, b_mn_major, C, ldc, bias, accumulate, gate);
+  if (rc < 0) return fail("s2vt_gemm_bf16_gated: unsupported configuration");
+  return rc;
 }
 
 extern "C" int64_t s2vt_vocab_ce_ws_bytes(int R, int V) { return (int64_t)R * ceil_div(V, PBN) * (int64_t)sizeof(float2); }

@@ -301,7 +301,11 @@ int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int
                         void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate);
 void gemm_persist_set_max_ctas(int n);
 static thread_local int g_use_persistent = 1;
+static thread_local int g_high_priority = 0;      // 1: launch with the device's greatest priority as a launch attribute
 }
+
+
+extern "C" int s2vt_set_launch_priority(int high) { g_high_priority = high ? 1 : 0; return 0; }
 
 extern "C" int s2vt_gemm_bf16_set_mode(int max_ctas, int use_persistent) {
   gemm_persist_set_max_ctas(max_ctas);
@@ -372,7 +376,16 @@ extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,
 #define S2VT_LAUNCH_GEMM(AM, BMJ)                                                                                   \
   do {                                                                                                              \
     S2VT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<AM, BMJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
-    gemm_bf16_kernel<AM, BMJ><<<grid, 256, GEMM_SMEM, st>>>(tmA, tmB, tmC, p);                                        \
+    cudaLaunchConfig_t cfg{};                                                                                       \
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = GEMM_SMEM; cfg.stream = st;                \
+    cudaLaunchAttribute attr[1];                                                                                    \
+    if (g_high_priority) {                                                                                          \
+      int least = 0, greatest = 0;                                                                                  \
+      S2VT_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));                                         \
+      attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = greatest;                                    \
+      cfg.attrs = attr; cfg.numAttrs = 1;                                                                           \
+    }                                                                                                               \
+    S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<AM, BMJ>, tmA, tmB, tmC, p));                         \
   } while (0)
   if (!a_mn_major && !b_mn_major) S2VT_LAUNCH_GEMM(false, false);
   else if (a_mn_major && !b_mn_major) S2VT_LAUNCH_GEMM(true, false);

@@ -147,19 +147,61 @@ __global__ void adam_prepare_kernel(int* __restrict__ step, const float* __restr
   hyper[1] = (float)(1.0 / sqrt(bc2));
 }
 
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float beta1, float beta2, float eps, float step_size, float inv_bc2_sqrt,
-                            float grad_scale, __nv_bfloat16* __restrict__ shadow, const float* __restrict__ hyper) {
+// A CTA handles chunks of 256 threads x 4 float4 = 4096 consecutive elements: 16-byte accesses, the four loads of every array issued
+// before the first use.  Normally one chunk per CTA; under s2vt_set_bulk_cta_cap (update beside a recurrence sweep) a capped grid
+// strides over the chunks.
+constexpr int ADAM_ELEMS_PER_CTA = 4096;
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float beta1, float beta2, float eps,
+                                                   float step_size, float inv_bc2_sqrt, float grad_scale,
+                                                   __nv_bfloat16* __restrict__ shadow, const float* __restrict__ hyper) {
   if (hyper) { step_size = hyper[0]; inv_bc2_sqrt = hyper[1]; }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi; v[i] = vi;
+  for (long long base = (long long)blockIdx.x * ADAM_ELEMS_PER_CTA; base < n; base += (long long)gridDim.x * ADAM_ELEMS_PER_CTA) {
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+    gi *= grad_scale;
+    mi = beta1 * mi + omb1 * gi;
+    vi = beta2 * vi + omb2 * gi * gi;
     const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
-    const float pi = p[i] - step_size * (mi / denom);
-    p[i] = pi;
+    pi = pi - step_size * (mi / denom);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (!shadow || (reinterpret_cast<uintptr_t>(shadow) & 7) == 0);
+  if (vec && base + ADAM_ELEMS_PER_CTA <= n) {
+    float4 G[4], M[4], V[4], P[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = base + ((long long)j * 256 + threadIdx.x) * 4;
+      G[j] = __ldcs(reinterpret_cast<const float4*>(g + i));
+      M[j] = *reinterpret_cast<const float4*>(m + i);
+      V[j] = *reinterpret_cast<const float4*>(v + i);
+      P[j] = *reinterpret_cast<const float4*>(p + i);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = base + ((long long)j * 256 + threadIdx.x) * 4;
+      upd(G[j].x, M[j].x, V[j].x, P[j].x); upd(G[j].y, M[j].y, V[j].y, P[j].y);
+      upd(G[j].z, M[j].z, V[j].z, P[j].z); upd(G[j].w, M[j].w, V[j].w, P[j].w);
+      *reinterpret_cast<float4*>(m + i) = M[j];
+      *reinterpret_cast<float4*>(v + i) = V[j];
+      *reinterpret_cast<float4*>(p + i) = P[j];
+      if (shadow) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(P[j].x, P[j].y), b = __floats2bfloat162_rn(P[j].z, P[j].w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(shadow + i) = pk;
+      }
+    }
+    continue;
+  }
+  const long long end = base + ADAM_ELEMS_PER_CTA < n ? base + ADAM_ELEMS_PER_CTA : n;
+  for (long long i = base + threadIdx.x; i < end; i += 256) {
+    float mi = m[i], vi = v[i], pi = p[i];
+    upd(g[i], mi, vi, pi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
     if (shadow) shadow[i] = __float2bfloat16(pi);
+  }
   }
 }
 
@@ -201,8 +243,14 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
 
 }  // namespace s2vt
 
+namespace s2vt {
+static thread_local int g_bulk_cta_cap = 0;
+int bulk_cta_cap() { return g_bulk_cta_cap; }
+}  // namespace s2vt
+
 using namespace s2vt;
 
+extern "C" int s2vt_set_bulk_cta_cap(int n) { g_bulk_cta_cap = n > 0 ? n : 0; return 0; }
 extern "C" int s2vt_abi_version(void) { return S2VT_ABI_VERSION; }
 extern "C" const char* s2vt_last_error(void) { return err_buf(); }
 extern "C" int64_t s2vt_launch_count(void) { return (int64_t)g_launches.load(); }
@@ -271,8 +319,8 @@ extern "C" int s2vt_adam_f32(void* stream, float* p, const float* g, float* m, f
   const double bc1 = 1.0 - pow((double)beta1, step_count), bc2 = 1.0 - pow((double)beta2, step_count);
   const float step_size = (float)((double)lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  int blocks = ceil_div(n, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  int blocks = (int)ceil_div(n, (int64_t)ADAM_ELEMS_PER_CTA);
+  if (bulk_cta_cap() > 0 && blocks > bulk_cta_cap()) blocks = bulk_cta_cap();
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, step_size, inv_bc2_sqrt, grad_scale,
                                                         (__nv_bfloat16*)bf16_copy, nullptr);
   S2VT_CHECK_LAUNCH();
@@ -290,8 +338,8 @@ extern "C" int s2vt_adam_f32_dev(void* stream, float* p, const float* g, float* 
                                  float beta1, float beta2, float eps, const float* hyper_dev, float grad_scale, void* bf16_copy) {
   S2VT_REQUIRE(p && g && m && v && hyper_dev, "s2vt_adam_f32_dev: null pointer");
   if (n == 0) return 0;
-  int blocks = ceil_div(n, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  int blocks = (int)ceil_div(n, (int64_t)ADAM_ELEMS_PER_CTA);
+  if (bulk_cta_cap() > 0 && blocks > bulk_cta_cap()) blocks = bulk_cta_cap();
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, 0.f, 0.f, grad_scale, (__nv_bfloat16*)bf16_copy,
                                                         hyper_dev);
   S2VT_CHECK_LAUNCH();

@@ -232,7 +232,10 @@ extern "C" int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int
   if (out2) S2VT_CHECK_CUDA(cudaMemsetAsync(out2, 0, sizeof(float) * N, st));
   if (N % 8 == 0 && ld % 8 == 0 && aligned16(X_bf16)) {
     const int gx8 = ceil_div(N, 256);
-    int gy8 = ceil_div(148 * 4, gx8);                   // ~4 blocks of 256 threads per SM in total
+    int gy8 = ceil_div(148 * 4, gx8);                   // at least ~4 blocks of 256 threads per SM in total ...
+    const int gy_short = ceil_div(M, 128);              // ... and at most 128 rows (64 KB) per block: blocks that live a microsecond or two
+    if (gy8 < gy_short) gy8 = gy_short;                 // give their SM slots back to the wave front's coupling products at once
+    if (bulk_cta_cap() > 0) gy8 = bulk_cta_cap() / gx8;  // beside a recurrence sweep: all blocks resident at once, slots left over
     const int max_gy8 = ceil_div(M, 32);
     if (gy8 > max_gy8) gy8 = max_gy8;
     if (gy8 < 1) gy8 = 1;

@@ -118,6 +118,15 @@ class DataParallelTrainer:
         self._eager_steps = 0
         self._pool = None
         self.max_graphs = 8
+        self._execs: List[int] = []
+
+    def __del__(self):
+        try:
+            from .lib import load
+            for e in getattr(self, "_execs", []):
+                load().s2vt_graph_exec_destroy(e)
+        except Exception:                        # interpreter shutdown
+            pass
 
     def _bucket_ready(self, bucket: str) -> None:
         """Called by backward once every kernel producing `bucket`'s gradients has been enqueued (and nothing later in the step
@@ -140,7 +149,9 @@ class DataParallelTrainer:
         loss.backward()
         self.reducer.finish()
         self.opt.finish_step()
-        return loss
+        # (detached: a caller that keeps the loss must not keep this step's autograd graph -- and with it the parameters' AccumulateGrad
+        # nodes, which are bound to the stream they were created on -- alive into a later step's graph capture)
+        return loss.detach()
 
     def step(self, feats, targets, mask=None):
         from . import ops
@@ -154,11 +165,14 @@ class DataParallelTrainer:
                 self._eager_steps += 1
                 return self._step_eager(feats, targets, mask)
             ent = self._capture(key, feats, targets, mask)
-        graph, loss, n_launch, _keep = ent
+        graph, loss, n_launch, _keep, exec_ = ent
         self.opt.sync_lr()
-        graph.replay()
+        from .lib import load, check, stream_ptr
+        if exec_ is not None:
+            check(load().s2vt_graph_launch(exec_, stream_ptr(feats.device)), "s2vt_graph_launch")
+        else:
+            graph.replay()
         self.opt.note_replayed_step()
-        from .lib import load
         load().s2vt_add_launch_count(n_launch)
         return loss
 
@@ -168,7 +182,11 @@ class DataParallelTrainer:
         host_step, epoch = f["step"], None
         self.opt.sync_lr()
         torch.cuda.synchronize(feats.device)
-        graph = torch.cuda.CUDAGraph()
+        # The executable graph is instantiated here, not by torch: torch passes no cudaGraphInstantiateFlagUseNodePriority, and without
+        # it every node runs at the launch stream's priority -- the wave front's coupling products (high-priority streams / launch
+        # attribute) would queue behind the CTAs of the bulk weight-gradient products.  S2VT_GRAPH_NODE_PRIORITY=0: torch's replay.
+        own = os.environ.get("S2VT_GRAPH_NODE_PRIORITY", "1") != "0"
+        graph = torch.cuda.CUDAGraph(keep_graph=True) if own else torch.cuda.CUDAGraph()
         n0 = launch_count()
         with torch.cuda.graph(graph, pool=self._pool):
             loss = self._step_eager(feats, targets, mask)
@@ -176,6 +194,14 @@ class DataParallelTrainer:
         if self._pool is None:
             self._pool = graph.pool()
         f["step"] = host_step                    # capturing enqueued nothing: the step happens at replay
-        ent = (graph, loss, n_launch, (feats, targets))
+        exec_ = None
+        if own:
+            import ctypes
+            from .lib import load, check
+            out = ctypes.c_void_p()
+            check(load().s2vt_graph_instantiate(graph.raw_cuda_graph(), 1, ctypes.byref(out)), "s2vt_graph_instantiate")
+            exec_ = out.value
+            self._execs.append(exec_)
+        ent = (graph, loss, n_launch, (feats, targets), exec_)
         self._graphs[key] = ent
         return ent

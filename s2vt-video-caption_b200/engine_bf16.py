@@ -18,6 +18,10 @@ from . import ops
 from .lib import dense, rowmap
 
 BF = torch.bfloat16
+# SM budget of the work that runs beside the two resident BPTT sweeps (96 of 148 SMs at B = 64): persistent GEMM CTAs (one per SM) and
+# CTAs of the memory-bound kernels (they share SMs with GEMM CTAs).  What is left over serves the wave front's coupling products.
+BULK_CTAS = int(_os.environ.get("S2VT_BULK_CTAS", "28"))
+BULK_ELT_CTAS = int(_os.environ.get("S2VT_BULK_ELT_CTAS", "104"))
 
 
 def supported(H: int, E: int, F: int, V: int) -> bool:
@@ -27,23 +31,65 @@ def supported(H: int, E: int, F: int, V: int) -> bool:
 
 # ------------------------------------------------------------------------------------------------ thin wrappers
 def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, cmap, out_bf16=False, bias=None, accumulate=False, a_off=0, b_off=0, c_off=0,
-         short_ctas=False):
-    """short_ctas: use the one-tile-per-CTA kernel.  Required for products that run BESIDE a recurrence sweep: a persistent CTA
-    keeps its SM for the whole product, and the sweep's 16-CTA clusters could not be placed until it retires."""
-    persistent = not short_ctas and cmap.inner == 1 and cmap.stride_inner == 0         # the library routes dense outputs there
+         short_ctas=False, urgent=False, bulk=False):
+    """short_ctas: use the one-tile-per-CTA kernel (products beside a recurrence sweep whose clusters may not be resident yet: a
+    persistent CTA keeps its SM for the whole product and the sweep's 16-CTA clusters could not be placed until it retires).
+    bulk: a big product beside two RESIDENT sweeps that nothing on the serial chain waits for (weight gradients): the persistent kernel
+    on at most BULK_CTAS SMs.  CTAs are dispatched in launch order -- stream and graph-node priorities do not reorder them, measured
+    with tools/probe_priority.py -- so a product with more CTAs than free slots would keep every later kernel, i.e. the wave front's
+    coupling products, waiting until its last CTA is placed; a capped persistent grid is resident at once and leaves SMs over."""
+    lib = L.load()
+    dense_c = cmap.inner == 1 and cmap.stride_inner == 0
+    bulk = bulk and dense_c and BULK_CTAS > 0
+    short_ctas = short_ctas and not bulk
+    persistent = not short_ctas and dense_c                                             # the library routes dense outputs there
     tag = "gemm_bf16_%s[%dx%dx%d %s%s%s]" % ("persist" if persistent else "tile", M, N, K, "T" if a_mn else "N", "T" if b_mn else "N",
                                              " bf16out" if out_bf16 else "")
-    lib = L.load()
     if short_ctas:
         lib.s2vt_gemm_bf16_set_mode(0, 0)
+    elif bulk:
+        lib.s2vt_gemm_bf16_set_mode(BULK_CTAS, 1)
+    if urgent:                                     # (launch attribute; kept for tools/probe_priority.py -- no measurable effect)
+        lib.s2vt_set_launch_priority(1)
     try:
         with ops._timed(tag, 2.0 * M * N * K, 2.0 * (M * K + N * K) + (2.0 if out_bf16 else 4.0) * M * N):
             rc = lib.s2vt_gemm_bf16(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), lda, int(a_mn), L.ptr(B, b_off), ldb, int(b_mn),
                                     L.ptr(C, c_off), cmap, int(out_bf16), L.ptr(bias), int(accumulate))
     finally:
-        if short_ctas:
+        if short_ctas or bulk:
             lib.s2vt_gemm_bf16_set_mode(0, 1)
+        if urgent:
+            lib.s2vt_set_launch_priority(0)
     L.check(rc, "s2vt_gemm_bf16")
+
+
+def gemm_gated(M, N, K, A, lda, B, ldb, b_mn, C, ldc, rows, wait, wait_val, done, ready, k0=0, bias=None, accumulate=False,
+               max_ctas=20, reverse_m=False, a_off=0, b_off=0, c_off=0):
+    """s2vt_gemm_bf16_gated: `rows` = chunk boundaries in rows of this product (0 .. M); wait / done / ready = counter rows, chunk 0 of
+    this product being their element k0."""
+    arr = (ctypes.c_int * len(rows))(*rows)
+    with ops._timed("gemm_bf16_gated[%dx%dx%d N%s]" % (M, N, K, "T" if b_mn else "N"), 2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N):
+        rc = L.load().s2vt_gemm_bf16_gated(L.stream_ptr(A.device), M, N, K, L.ptr(A, a_off), lda, L.ptr(B, b_off), ldb, int(b_mn),
+                                           L.ptr(C, c_off), ldc, L.ptr(bias), int(accumulate), int(max_ctas), int(reverse_m),
+                                           len(rows) - 1, arr, L.ptr(wait, k0), int(wait_val), L.ptr(done, k0), L.ptr(ready, k0))
+    L.check(rc, "s2vt_gemm_bf16_gated")
+
+
+class beside_sweeps:
+    """Context for the memory-bound kernels (column sums, Adam) enqueued while two sweeps are resident: grids of at most BULK_ELT_CTAS
+    CTAs (s2vt_set_bulk_cta_cap), for the reason given in gemm(bulk=True)."""
+
+    def __init__(self, on: bool = True):
+        self.on = on and BULK_ELT_CTAS > 0
+
+    def __enter__(self):
+        if self.on:
+            L.load().s2vt_set_bulk_cta_cap(BULK_ELT_CTAS)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            L.load().s2vt_set_bulk_cta_cap(0)
 
 
 def cast(src: torch.Tensor, rows: int, cols: int, want_t: bool = False, want_plain: bool = True):
@@ -180,12 +226,31 @@ def ce_dlogits_inplace(logits_bf, R, V, lse, targets_full, t_off, tmap, gscale):
 WAVEFRONT = _os.environ.get("S2VT_WAVEFRONT", "1") != "0"       # run the two layers' sweeps side by side, a time chunk apart (False: one whole sweep after the other)
 
 
-WAVE_SPLITS = (3, 3)  # time chunks before / after step L (the embedding half of word_rnn's input starts at L: a chunk never straddles it)
+MAX_SYNC = 64                # S2VT_MAX_SYNC of the header
+# The product coupling the two sweeps: one resident gated launch (s2vt_gemm_bf16_gated) on this many SMs, or ("0") one launch per chunk
+# released by stream memory operations.
+WAVE_SERVER = _os.environ.get("S2VT_WAVE_SERVER", "1") != "0"
+FWD_SERVER_CTAS = int(_os.environ.get("S2VT_FWD_SERVER_CTAS", "24"))
+BWD_SERVER_CTAS = int(_os.environ.get("S2VT_BWD_SERVER_CTAS", "20"))
 
 
-def _time_bounds(Lq: int, T: int):
-    n0, n1 = [int(x) for x in _os.environ["S2VT_WAVE_SPLITS"].split(",")] if "S2VT_WAVE_SPLITS" in _os.environ else WAVE_SPLITS
-    return sorted(set([round(i * Lq / n0) for i in range(n0 + 1)] + [Lq + round(i * (T - Lq) / n1) for i in range(n1 + 1)]))
+def _time_bounds(Lq: int, T: int, backward: bool = False):
+    """Chunk boundaries of the wave front.  The trailing sweep can never be ahead of the leading one by less than a chunk plus its
+    coupling product, at the start and at the end of the sequence alike, so chunks are short (S2VT_WAVE_CHUNK steps, default 10; the
+    very first one half of that) -- limited by the product's efficiency at few rows and by MAX_SYNC.  No chunk straddles step L (the
+    embedding half of word_rnn's input starts there).  For BPTT the same pattern is laid out from the end of the sequence."""
+    c = max(2, int(_os.environ.get("S2VT_WAVE_CHUNK", "10")))
+    c = max(c, -(-T // (MAX_SYNC - 2)))
+    pos, p = [0], c // 2 + 1
+    while p < T:
+        pos.append(p)
+        p += c
+    if T - pos[-1] < c // 2 and len(pos) > 1:
+        pos.pop()
+    pos.append(T)
+    cut = (T - Lq) if backward else Lq                       # position of step L in processing order
+    pos = sorted(set([x for x in pos if abs(x - cut) >= 3 or x in (0, T)] + [cut]))
+    return [T - x for x in pos][::-1] if backward else pos
 
 
 def _wave_tiles(which: str):
@@ -199,10 +264,11 @@ _COUNTERS = {}
 
 
 def _wave_counters(dev) -> torch.Tensor:
-    """[4, 16] u32 (as int32) device counters: rows = forward signal / ready, backward signal / ready (s2vt_lstm_fwd_bf16_sync)."""
+    """[6, MAX_SYNC] u32 (as int32) device counters: rows = forward signal / ready, backward signal / ready (s2vt_lstm_fwd_bf16_sync),
+    forward / backward completion scratch of the gated coupling product (s2vt_gemm_bf16_gated)."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _COUNTERS:
-        _COUNTERS[key] = torch.zeros(4, 16, dtype=torch.int32, device=dev)
+        _COUNTERS[key] = torch.zeros(6, MAX_SYNC, dtype=torch.int32, device=dev)
     return _COUNTERS[key]
 
 
@@ -224,6 +290,7 @@ def _wavefront_forward(P, S, B, Lq, H, E, T, Bp, pre1, out1, g1, c1, emb_seq, pr
     W2 = S["word_rnn.weight_ih_l0"]
     ctr = _wave_counters(dev)
     ctr[0:2].zero_()
+    ctr[4].zero_()
     bounds = _time_bounds(Lq, T)
     n_arrive = (H // 32) * ((B + 15) // 16)
     ntl_lead, ntl_trail = _wave_tiles("FWD")
@@ -240,16 +307,34 @@ def _wavefront_forward(P, S, B, Lq, H, E, T, Bp, pre1, out1, g1, c1, emb_seq, pr
                      sync=(bounds, None, ctr[1], 1))
 
     def products():
+        se = _aux_stream(dev, "wave_emb")
+        with torch.cuda.stream(se):
+            se.wait_event(ev0)
+            # embedding half of word_rnn's input product: no dependence on vid_rnn at all, needed from step L on
+            gemm(R, 4 * H, E, emb_seq, E, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"], c_off=Lq * B * 4 * H, short_ctas=True,
+                 bulk=WAVE_SERVER)
+            ev_emb = torch.cuda.Event()
+            ev_emb.record(se)
         with torch.cuda.stream(sg):
             sg.wait_event(ev0)
-            # embedding half of word_rnn's input product: no dependence on vid_rnn at all
-            gemm(R, 4 * H, E, emb_seq, E, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"], c_off=Lq * B * 4 * H, short_ctas=True)
-            for k in range(len(bounds) - 1):
-                t0, t1 = bounds[k], bounds[k + 1]
-                L.check(lib.s2vt_stream_wait_value32(sg.cuda_stream, L.ptr(ctr, k), n_arrive), "s2vt_stream_wait_value32")
-                gemm((t1 - t0) * B, 4 * H, H, out1, H, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"] if t1 <= Lq else None,
-                     accumulate=t0 >= Lq, a_off=t0 * B * H, b_off=E, c_off=t0 * B * 4 * H, short_ctas=True)
-                L.check(lib.s2vt_stream_write_value32(sg.cuda_stream, L.ptr(ctr, 16 + k), 1), "s2vt_stream_write_value32")
+            if WAVE_SERVER:
+                kL = bounds.index(Lq)
+                # steps < L: pre2 = out1 W^T + b;  steps >= L: added onto the embedding half (which carries the bias)
+                gemm_gated(Lq * B, 4 * H, H, out1, H, W2, E + H, False, pre2, 4 * H, [t * B for t in bounds[:kL + 1]], ctr[0], n_arrive,
+                           ctr[4], ctr[1], bias=S["b2"], max_ctas=FWD_SERVER_CTAS, b_off=E)
+                sg.wait_event(ev_emb)
+                gemm_gated((T - Lq) * B, 4 * H, H, out1, H, W2, E + H, False, pre2, 4 * H, [(t - Lq) * B for t in bounds[kL:]], ctr[0],
+                           n_arrive, ctr[4], ctr[1], k0=kL, accumulate=True, max_ctas=FWD_SERVER_CTAS, a_off=Lq * B * H, b_off=E,
+                           c_off=Lq * B * 4 * H)
+            else:
+                for k in range(len(bounds) - 1):
+                    t0, t1 = bounds[k], bounds[k + 1]
+                    L.check(lib.s2vt_stream_wait_value32(sg.cuda_stream, L.ptr(ctr, k), n_arrive), "s2vt_stream_wait_value32")
+                    if t0 == Lq:
+                        sg.wait_event(ev_emb)
+                    gemm((t1 - t0) * B, 4 * H, H, out1, H, False, W2, E + H, False, pre2, dense(4 * H), bias=S["b2"] if t1 <= Lq else None,
+                         accumulate=t0 >= Lq, a_off=t0 * B * H, b_off=E, c_off=t0 * B * 4 * H, short_ctas=True)
+                    L.check(lib.s2vt_stream_write_value32(sg.cuda_stream, L.ptr(ctr, MAX_SYNC + k), 1), "s2vt_stream_write_value32")
             ev_g.record(sg)
 
     _run_coupled(("fwd", dev.index, B, Lq, H, E), trailing_sweep, products)
@@ -287,12 +372,14 @@ def _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, events):
     ev_dout2, ev_dg2, ev_dout1, ev_dg1 = events
     sg, s1 = _aux_stream(dev, "wave_bgemm"), _aux_stream(dev, "wave_bl1")
     ntl_lead, ntl_trail = _wave_tiles("BWD")
-    bounds = _time_bounds(Lq, T)
+    bounds = _time_bounds(Lq, T, backward=True)
     n_arrive = (H // 32) * ((B + 15) // 16)
     W2 = S["word_rnn.weight_ih_l0"]
+    ev_first = torch.cuda.Event()
     with torch.cuda.stream(chain):
         ctr = _wave_counters(dev)
         ctr[2:4].zero_()
+        ctr[5].zero_()
         gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=Lq * B * H)
         ev_dout2.record(chain)
         lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2, tiles_per_cluster=ntl_lead,
@@ -308,17 +395,31 @@ def _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, events):
     def products():
         with torch.cuda.stream(sg):
             sg.wait_event(ev_dout2)
-            for k in range(len(bounds) - 2, -1, -1):
-                t0, t1 = bounds[k], bounds[k + 1]
-                L.check(lib.s2vt_stream_wait_value32(sg.cuda_stream, L.ptr(ctr, 32 + k), n_arrive), "s2vt_stream_wait_value32")
-                gemm((t1 - t0) * B, H, 4 * H, dg2, 4 * H, False, W2, E + H, True, dout1, dense(H), a_off=t0 * B * 4 * H, b_off=E,
-                     c_off=t0 * B * H, short_ctas=True)
-                L.check(lib.s2vt_stream_write_value32(sg.cuda_stream, L.ptr(ctr, 48 + k), 1), "s2vt_stream_write_value32")
+            if WAVE_SERVER:
+                gemm_gated(T * B, H, 4 * H, dg2, 4 * H, W2, E + H, True, dout1, H, [t * B for t in bounds], ctr[2], n_arrive, ctr[5], ctr[3],
+                           max_ctas=BWD_SERVER_CTAS, reverse_m=True, b_off=E)
+            else:
+                for k in range(len(bounds) - 2, -1, -1):
+                    t0, t1 = bounds[k], bounds[k + 1]
+                    L.check(lib.s2vt_stream_wait_value32(sg.cuda_stream, L.ptr(ctr, 2 * MAX_SYNC + k), n_arrive), "s2vt_stream_wait_value32")
+                    gemm((t1 - t0) * B, H, 4 * H, dg2, 4 * H, False, W2, E + H, True, dout1, dense(H), a_off=t0 * B * 4 * H, b_off=E,
+                         c_off=t0 * B * H, short_ctas=True)
+                    L.check(lib.s2vt_stream_write_value32(sg.cuda_stream, L.ptr(ctr, 3 * MAX_SYNC + k), 1), "s2vt_stream_write_value32")
+                    if k == len(bounds) - 2:
+                        ev_first.record(sg)
             ev_dout1.record(sg)
 
     _run_coupled(("bwd", dev.index, B, Lq, H, E), trailing_sweep, products)
     chain.wait_event(ev_dg1)
     chain.wait_event(ev_dout1)
+    if WAVE_SERVER:
+        # the bulk products of the caller's stream start once word_rnn's sweep has finished its first chunk: both sweeps and the coupling
+        # kernel are resident by then, and whatever the bulk CTAs do to the dispatch queue no longer matters to the wave front
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev_dout2)
+        L.check(lib.s2vt_stream_wait_value32(cur.cuda_stream, L.ptr(ctr, 2 * MAX_SYNC + len(bounds) - 2), n_arrive), "s2vt_stream_wait_value32")
+        return ev_dout2
+    return ev_first            # the trailing sweep is under way: from here on the free SMs belong to the weight-gradient products
 
 
 def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, ce=None):
@@ -403,8 +504,12 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     dout1 = torch.empty(T * B, H, device=dev)
     dg1 = torch.empty(T * B, 4 * H, dtype=BF, device=dev)
     ev_dout2, ev_dg2, ev_dout1, ev_dg1 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-    if wave_ok(B, Lq):
-        _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, (ev_dout2, ev_dg2, ev_dout1, ev_dg1))
+    wave = wave_ok(B, Lq)
+    capped = wave and not WAVE_SERVER            # (with the resident coupling kernel the bulk products need no SM budget)
+    if wave:
+        # (a 13000 x 512 x 5056 weight-gradient product launched now would hold every free SM for 150 us and starve the first chunk's
+        # coupling product, i.e. delay the trailing sweep by as much: it starts once that product is through)
+        ev_dout2 = _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, (ev_dout2, ev_dg2, ev_dout1, ev_dg1))
     else:
         with torch.cuda.stream(chain):
             gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
@@ -419,23 +524,26 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     cur.wait_event(ev_dout2)
     gW = _new("out_linear.weight", V, H)
     gb = _new("out_linear.bias", V)
-    gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True)
-    colsum_bf16(dl_bf, R, V, V, gb)
-    G["out_linear.weight"], G["out_linear.bias"] = gW, gb
-    _ready("out_linear")
+    with beside_sweeps(capped):
+        gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True, bulk=capped)
+        colsum_bf16(dl_bf, R, V, V, gb)
+        G["out_linear.weight"], G["out_linear.bias"] = gW, gb
+        _ready("out_linear")
     # ---- word_rnn weight / bias / embedding gradients (beside the vid_rnn sweep)
     cur.wait_event(ev_dg2)
     gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
     gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
     gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
     gE = _new("embedding.weight", V, E)
-    gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E, short_ctas=True)
-    gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H, short_ctas=True)
-    gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H, short_ctas=True)
-    colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
-    G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
     demb = torch.empty(R, E, device=dev)
-    gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True)
+    with beside_sweeps(capped):
+        gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E, short_ctas=True, bulk=capped)
+        gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H, short_ctas=True, bulk=capped)
+        gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H, short_ctas=True, bulk=capped)
+        colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
+        G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
+        gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True,
+             bulk=capped)
     cur.wait_event(ev_dout1)
     _ready("word_rnn")                                                          # (after the last readers of word_rnn's weights)
     gE.zero_()

@@ -53,6 +53,14 @@ SIGNATURES = {
     "s2vt_lstm_bf16_set_tiles_per_cluster": (_i, [_i]),
     "s2vt_lstm_fwd_bf16_sync": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _u32]),
     "s2vt_lstm_bwd_bf16_sync": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _u32]),
+    "s2vt_set_launch_priority": (_i, [_i]),
+    "s2vt_set_bulk_cta_cap": (_i, [_i]),
+    "s2vt_gemm_bf16_gated": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _vp, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp]),
+    "s2vt_graph_instantiate": (_i, [_vp, _i, _vp]),
+    "s2vt_graph_launch": (_i, [_vp, _vp]),
+    "s2vt_graph_exec_destroy": (_i, [_vp]),
+    "s2vt_graph_kernel_priorities": (_i, [_vp, _vp, _i, _vp]),
+    "s2vt_timestamp": (_i, [_vp, _vp]),
     "s2vt_stream_wait_value32": (_i, [_vp, _vp, _u32]),
     "s2vt_stream_write_value32": (_i, [_vp, _vp, _u32]),
     "s2vt_lstm_bwd_bf16_chunk": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i]),

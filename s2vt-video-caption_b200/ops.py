@@ -43,11 +43,24 @@ class profile:
         return out
 
 
+MARKS = None             # tools/timeline_step.py: dict(buf=int64 device tensor, names=[...]) -> %globaltimer stamps around every call
+
+
+def _mark(name):
+    m = MARKS
+    i = len(m["names"])
+    if i < m["buf"].numel():
+        m["names"].append(name)
+        L.load().s2vt_timestamp(L.stream_ptr(m["buf"].device), L.ptr(m["buf"], i))
+
+
 class _timed:
     def __init__(self, tag, flops=0.0, nbytes=0.0):
         self.tag, self.flops, self.nbytes = tag, flops, nbytes
 
     def __enter__(self):
+        if MARKS is not None:
+            _mark("B " + self.tag)
         if _PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -55,6 +68,8 @@ class _timed:
         return self
 
     def __exit__(self, *exc):
+        if MARKS is not None:
+            _mark("E " + self.tag)
         if _PROFILE is not None and exc[0] is None:
             self.e1.record()
             _PROFILE.records.append((self.tag, self.e0, self.e1, self.flops, self.nbytes))

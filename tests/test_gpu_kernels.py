@@ -131,6 +131,64 @@ def test_gemm_bf16_persistent_back_to_back_launches(dev):
     assert (C.double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("b_mn,reverse_m,accumulate", [(False, False, False), (True, True, False), (False, False, True), (True, False, True)])
+def test_gemm_bf16_gated_matches_plain_product(dev, b_mn, reverse_m, accumulate):
+    """s2vt_gemm_bf16_gated with every chunk already released: the plain product, and every chunk's ready flag raised exactly once."""
+    from s2vt_b200 import engine_bf16 as EB
+    M, N, K = 1000, 512, 320                              # 8 row tiles (the last one partial), chunk bounds off the tile grid
+    g = torch.Generator().manual_seed(17)
+    A = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
+    Bm = torch.randn(N, K, generator=g).to(dev).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(dev)
+    rows = [0, 64, 200, 456, 999, 1000]
+    n = len(rows) - 1
+    ctr = torch.zeros(3, EB.MAX_SYNC, dtype=torch.int32, device=dev)
+    ctr[0, :n] = 7
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    C = C0.clone() if accumulate else torch.full((M, N), float("nan"), device=dev)
+    Bs = Bm.T.contiguous() if b_mn else Bm
+    EB.gemm_gated(M, N, K, A, K, Bs, N if b_mn else K, b_mn, C, N, rows, ctr[0], 7, ctr[1], ctr[2], bias=None if accumulate else bias,
+                  accumulate=accumulate, max_ctas=5, reverse_m=reverse_m)
+    torch.cuda.synchronize()
+    ref = A.double() @ Bm.double().T + (C0.double() if accumulate else bias.double())
+    assert _rel(C, ref.float()) < 1e-5
+    assert ctr[2, :n].tolist() == [1] * n and ctr[2, n:].abs().sum().item() == 0
+    assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+
+
+def test_gemm_bf16_gated_waits_for_its_chunks(dev):
+    """The gated product is launched FIRST and spins; its chunks are released one by one from another stream (last chunk first, as a
+    backward sweep does) behind copies that fill the corresponding rows of A -- a tile read before its release would see zeros."""
+    from s2vt_b200 import engine_bf16 as EB
+    M, N, K = 1536, 256, 512
+    g = torch.Generator().manual_seed(19)
+    A_src = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
+    Bm = torch.randn(N, K, generator=g).to(dev).to(torch.bfloat16)
+    A = torch.zeros_like(A_src)
+    rows = [0, 300, 700, 1100, 1536]
+    n = len(rows) - 1
+    ctr = torch.zeros(3, EB.MAX_SYNC, dtype=torch.int32, device=dev)
+    C = torch.full((M, N), float("nan"), device=dev)
+    lib = L.load()
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):                          # first launches load kernel code, which can wait for the device to drain:
+        torch.cuda._sleep(1000)                            # do them before a spinning kernel is resident
+        A[:8].copy_(A_src[:8])
+        A[:8].zero_()
+        L.check(lib.s2vt_stream_write_value32(side.cuda_stream, L.ptr(ctr[0], EB.MAX_SYNC - 1), 0), "s2vt_stream_write_value32")
+    torch.cuda.synchronize()
+    EB.gemm_gated(M, N, K, A, K, Bm, K, False, C, N, rows, ctr[0], 1, ctr[1], ctr[2], max_ctas=4, reverse_m=True)
+    with torch.cuda.stream(side):
+        for k in range(n - 1, -1, -1):
+            torch.cuda._sleep(200000)                      # ~0.1 ms between releases
+            A[rows[k]:rows[k + 1]].copy_(A_src[rows[k]:rows[k + 1]])
+            L.check(lib.s2vt_stream_write_value32(side.cuda_stream, L.ptr(ctr[0], k), 1), "s2vt_stream_write_value32")
+    torch.cuda.synchronize()
+    assert _rel(C, (A_src.double() @ Bm.double().T).float()) < 1e-5
+    assert ctr[2, :n].tolist() == [1] * n
+    assert lib.s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+
+
 def test_gemm_bf16_epilogues(dev):
     C, ref = _gemm_bf16(dev, 300, 200, 256, False, False, out_bf16=True)
     assert (C.double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()

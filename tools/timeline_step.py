@@ -45,6 +45,38 @@ def main():
     t_all = time.perf_counter() - t0
     print("host enqueue %.3f ms/step, wall incl. device %.3f ms/step" % (1e3 * t_enq / args.steps, 1e3 * t_all / args.steps))
     print("device error flag:", s2vt_b200.load().s2vt_device_error_flag(None))
+    if trainer.use_graph and trainer._graphs:
+        import collections
+        import ctypes
+        ent = next(iter(trainer._graphs.values()))
+        if ent[4] is not None:
+            pr = (ctypes.c_int * 1024)()
+            n = ctypes.c_int(0)
+            s2vt_b200.load().s2vt_graph_kernel_priorities(ent[0].raw_cuda_graph(), pr, 1024, ctypes.byref(n))
+            print("kernel-node priorities of the captured step (priority: nodes):", dict(collections.Counter(pr[:min(n.value, 1024)])))
+    if trainer.use_graph:
+        # device-side timeline of a REPLAYED step: %globaltimer stamps captured into a fresh graph around every call
+        buf = torch.zeros(512, dtype=torch.int64, device=dev)
+        ops.MARKS = dict(buf=buf, names=[])
+        f, t, m = bench.synth_batch(args.batch, 999, device=dev)
+        trainer.step(f, t, m)                       # capture (+ first replay) with the stamps in
+        names = list(ops.MARKS["names"])
+        ops.MARKS = None
+        for _ in range(3):
+            trainer.step(f, t, m)
+        torch.cuda.synchronize()
+        ts = buf.cpu().tolist()[:len(names)]
+        t0g = min(ts)
+        open_ = {}
+        print("graph replay: step span %.1f us (with %d stamp kernels inside)" % ((max(ts) - t0g) / 1e3, len(names)))
+        for nm, tv in zip(names, ts):
+            kind, tag = nm[0], nm[2:]
+            if kind == "B":
+                open_.setdefault(tag, []).append(tv)
+            else:
+                b = open_[tag].pop(0)
+                print("%9.1f %9.1f %8.1f  %s" % ((b - t0g) / 1e3, (tv - t0g) / 1e3, (tv - b) / 1e3, tag))
+        print()
     with ops.profile() as prof:
         trainer.step(*batches[0])
         torch.cuda.synchronize()
