@@ -182,10 +182,10 @@ class DataParallelTrainer:
         host_step, epoch = f["step"], None
         self.opt.sync_lr()
         torch.cuda.synchronize(feats.device)
-        # The executable graph is instantiated here, not by torch: torch passes no cudaGraphInstantiateFlagUseNodePriority, and without
-        # it every node runs at the launch stream's priority -- the wave front's coupling products (high-priority streams / launch
-        # attribute) would queue behind the CTAs of the bulk weight-gradient products.  S2VT_GRAPH_NODE_PRIORITY=0: torch's replay.
-        own = os.environ.get("S2VT_GRAPH_NODE_PRIORITY", "1") != "0"
+        # S2VT_GRAPH_NODE_PRIORITY=1: instantiate the executable graph here with cudaGraphInstantiateFlagUseNodePriority (torch passes no
+        # such flag, so every node runs at the launch stream's priority).  Measured (tools/probe_priority.py): CTAs are dispatched in
+        # launch order with or without node priorities, so the default is torch's own replay; the wave front does not rely on priorities.
+        own = os.environ.get("S2VT_GRAPH_NODE_PRIORITY", "0") == "1"
         graph = torch.cuda.CUDAGraph(keep_graph=True) if own else torch.cuda.CUDAGraph()
         n0 = launch_count()
         with torch.cuda.graph(graph, pool=self._pool):

@@ -520,8 +520,14 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
             ev_dout1.record(chain)
             lstm_bwd(T, B, H, 0, dout1, saved["g1"], saved["c1"], S["vid_rnn.weight_hh_l0.T"], dg1)
             ev_dg1.record(chain)
+    # Everything below is off the serial chain.  Three independent groups -- out_linear | word_rnn + embedding | vid_rnn + feat_linear --
+    # each on its own stream (the caller's, and two side streams): beside the sweeps they share the free SMs, and once the sweeps are
+    # through, kernels that are too small to fill the machine alone (column sums, 32-tile products, per-bucket Adam) overlap.
+    sB, sC, sD = _aux_stream(dev, "bulk_b", 0), _aux_stream(dev, "bulk_c", 0), _aux_stream(dev, "bulk_d", 0)
     # ---- out_linear:  dW = dl^T h,  db = colsum(dl)   (beside the word_rnn sweep; released together with it)
     cur.wait_event(ev_dout2)
+    ev_bulk = torch.cuda.Event()
+    ev_bulk.record(cur)
     gW = _new("out_linear.weight", V, H)
     gb = _new("out_linear.bias", V)
     with beside_sweeps(capped):
@@ -530,48 +536,65 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
         G["out_linear.weight"], G["out_linear.bias"] = gW, gb
         _ready("out_linear")
     # ---- word_rnn weight / bias / embedding gradients (beside the vid_rnn sweep)
-    cur.wait_event(ev_dg2)
     gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
     gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
     gb2, gb2b = _new("word_rnn.bias_ih_l0", 4 * H), _new("word_rnn.bias_hh_l0", 4 * H)
     gE = _new("embedding.weight", V, E)
     demb = torch.empty(R, E, device=dev)
-    with beside_sweeps(capped):
-        gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E, short_ctas=True, bulk=capped)
-        gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H, short_ctas=True, bulk=capped)
-        gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H, short_ctas=True, bulk=capped)
-        colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
+    with torch.cuda.stream(sB):
+        sB.wait_event(ev_bulk)
+        sB.wait_event(ev_dg2)
+        with beside_sweeps(capped):
+            gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True,
+                 bulk=capped)
+            gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E, short_ctas=True, bulk=capped)
+            gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H, short_ctas=True,
+                 bulk=capped)
+            gemm(4 * H, H, (T - 1) * B, dg2, 4 * H, True, out2, H, True, gWhh2, dense(H), a_off=B * 4 * H, short_ctas=True, bulk=capped)
+            colsum_bf16(dg2, T * B, 4 * H, 4 * H, gb2, gb2b)
         G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
-        gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True,
-             bulk=capped)
-    cur.wait_event(ev_dout1)
-    _ready("word_rnn")                                                          # (after the last readers of word_rnn's weights)
-    gE.zero_()
-    ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
-    G["embedding.weight"] = gE
-    _ready("embedding")
-    # ---- vid_rnn (tail: the machine is free again)
+        sB.wait_event(ev_dout1)
+        _ready("word_rnn")                                                      # (after the last readers of word_rnn's weights)
+        gE.zero_()
+        ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
+        G["embedding.weight"] = gE
+        _ready("embedding")
+    # ---- vid_rnn and feat_linear (the machine is free again): the chain dg1 -> d xproj -> feat_linear on one stream, vid_rnn's own
+    # gradients on another
+    gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
+    gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)
+    gb1, gb1b = _new("vid_rnn.bias_ih_l0", 4 * H), _new("vid_rnn.bias_hh_l0", 4 * H)
+    gWf = _new("feat_linear.weight", H, F)
+    gbf = _new("feat_linear.bias", H)
+    dxp = torch.empty(B * Lq, H, dtype=BF, device=dev)
+    dfeats = torch.empty(B, Lq, F, device=dev) if need_dfeats else None
+    ev_dxp = torch.cuda.Event()
+    with torch.cuda.stream(sC):
+        sC.wait_event(ev_bulk)
+        sC.wait_event(ev_dg1)
+        # d xproj written back in batch-major row order so that it lines up with the bf16 features
+        gemm(Lq * B, H, 4 * H, dg1, 4 * H, False, S["vid_rnn.weight_ih_l0"], H, True, dxp, rowmap(B, H, Lq * H), out_bf16=True)
+        ev_dxp.record(sC)
+        gemm(H, F, B * Lq, dxp, H, True, saved["xb"], F, True, gWf, dense(F))
+        colsum_bf16(dxp, B * Lq, H, H, gbf)
+        G.update({"feat_linear.weight": gWf, "feat_linear.bias": gbf})
+        if need_dfeats:                                                          # dataloader.py:38 makes feats require grad
+            gemm(B * Lq, F, H, dxp, H, False, S["feat_linear.weight"], F, True, dfeats, dense(F))
+            G["feats"] = dfeats
+    with torch.cuda.stream(sD):
+        sD.wait_event(ev_bulk)
+        sD.wait_event(ev_dg1)
+        gemm(4 * H, H, Lq * B, dg1, 4 * H, True, xproj, H, True, gWih1, dense(H))
+        gemm(4 * H, H, (T - 1) * B, dg1, 4 * H, True, out1, H, True, gWhh1, dense(H), a_off=B * 4 * H)
+        colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1, gb1b)
+        G.update({"vid_rnn.weight_ih_l0": gWih1, "vid_rnn.weight_hh_l0": gWhh1, "vid_rnn.bias_ih_l0": gb1, "vid_rnn.bias_hh_l0": gb1b})
+        sD.wait_event(ev_dxp)
+        _ready("vid_rnn")                                                       # (after the last reader of vid_rnn's weights)
+    with torch.cuda.stream(sC):
+        _ready("feat_linear")
     cur.wait_event(ev_dg1)
     cur.wait_stream(chain)
-    gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
-    gemm(4 * H, H, Lq * B, dg1, 4 * H, True, xproj, H, True, gWih1, dense(H))
-    gWhh1 = _new("vid_rnn.weight_hh_l0", 4 * H, H)
-    gemm(4 * H, H, (T - 1) * B, dg1, 4 * H, True, out1, H, True, gWhh1, dense(H), a_off=B * 4 * H)
-    gb1, gb1b = _new("vid_rnn.bias_ih_l0", 4 * H), _new("vid_rnn.bias_hh_l0", 4 * H)
-    colsum_bf16(dg1, T * B, 4 * H, 4 * H, gb1, gb1b)
-    G.update({"vid_rnn.weight_ih_l0": gWih1, "vid_rnn.weight_hh_l0": gWhh1, "vid_rnn.bias_ih_l0": gb1, "vid_rnn.bias_hh_l0": gb1b})
-    # ---- feat_linear: d xproj written back in batch-major row order so that it lines up with the bf16 features
-    dxp = torch.empty(B * Lq, H, dtype=BF, device=dev)
-    gemm(Lq * B, H, 4 * H, dg1, 4 * H, False, S["vid_rnn.weight_ih_l0"], H, True, dxp, rowmap(B, H, Lq * H), out_bf16=True)
-    _ready("vid_rnn")                                                           # (after the last reader of vid_rnn's weights)
-    gWf = _new("feat_linear.weight", H, F)
-    gemm(H, F, B * Lq, dxp, H, True, saved["xb"], F, True, gWf, dense(F))
-    gbf = _new("feat_linear.bias", H)
-    colsum_bf16(dxp, B * Lq, H, H, gbf)
-    G.update({"feat_linear.weight": gWf, "feat_linear.bias": gbf})
-    if need_dfeats:                                                              # dataloader.py:38 makes feats require grad
-        dfeats = torch.empty(B, Lq, F, device=dev)
-        gemm(B * Lq, F, H, dxp, H, False, S["feat_linear.weight"], F, True, dfeats, dense(F))
-        G["feats"] = dfeats
-    _ready("feat_linear")
+    cur.wait_stream(sB)
+    cur.wait_stream(sC)
+    cur.wait_stream(sD)
     return G
