@@ -118,6 +118,7 @@ class DataParallelTrainer:
         self._eager_steps = 0
         self._pool = None
         self.max_graphs = 8
+        self._adam_stream = None
         self._execs: List[int] = []
 
     def __del__(self):
@@ -137,7 +138,13 @@ class DataParallelTrainer:
         a, b = self.ranges[bucket]
         a, b = a // 8 * 8, (b + 7) // 8 * 8
         if self.reducer.overlap:
-            with torch.cuda.stream(self.reducer.comm_stream):        # stream order: after this bucket's all-reduce
+            # behind this bucket's all-reduce, but on a stream of its own: the next bucket's all-reduce does not wait for this update
+            ev = torch.cuda.Event()
+            ev.record(self.reducer.comm_stream)
+            if self._adam_stream is None:
+                self._adam_stream = torch.cuda.Stream(device=self.reducer.flat.device)
+            with torch.cuda.stream(self._adam_stream):
+                self._adam_stream.wait_event(ev)
                 self.opt.step_range(a, b)
         else:
             self.opt.step_range(a, b)
@@ -148,6 +155,8 @@ class DataParallelTrainer:
         self.opt.begin_step()
         loss.backward()
         self.reducer.finish()
+        if self._adam_stream is not None:
+            torch.cuda.current_stream(self.reducer.flat.device).wait_stream(self._adam_stream)
         self.opt.finish_step()
         # (detached: a caller that keeps the loss must not keep this step's autograd graph -- and with it the parameters' AccumulateGrad
         # nodes, which are bound to the stream they were created on -- alive into a later step's graph capture)

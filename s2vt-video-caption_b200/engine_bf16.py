@@ -531,8 +531,8 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gW = _new("out_linear.weight", V, H)
     gb = _new("out_linear.bias", V)
     with beside_sweeps(capped):
+        colsum_bf16(dl_bf, R, V, V, gb)            # (first: behind the product's thousands of queued CTAs it would hold the bucket back)
         gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True, bulk=capped)
-        colsum_bf16(dl_bf, R, V, V, gb)
         G["out_linear.weight"], G["out_linear.bias"] = gW, gb
         _ready("out_linear")
     # ---- word_rnn weight / bias / embedding gradients (beside the vid_rnn sweep)
@@ -545,8 +545,13 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
         sB.wait_event(ev_bulk)
         sB.wait_event(ev_dg2)
         with beside_sweeps(capped):
+            # embedding first: its bucket is one of the two big ones (V x E), and in a data-parallel run its all-reduce should start early
             gemm(R, E, 4 * H, dg2, 4 * H, False, S["word_rnn.weight_ih_l0"], E + H, True, demb, dense(E), a_off=Lq * B * 4 * H, short_ctas=True,
                  bulk=capped)
+            gE.zero_()
+            ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
+            G["embedding.weight"] = gE
+            _ready("embedding")
             gemm(4 * H, H, T * B, dg2, 4 * H, True, out1, H, True, gWih2, dense(E + H), c_off=E, short_ctas=True, bulk=capped)
             gemm(4 * H, E, R, dg2, 4 * H, True, saved["emb_seq"], E, True, gWih2, dense(E + H), a_off=Lq * B * 4 * H, short_ctas=True,
                  bulk=capped)
@@ -555,10 +560,6 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
         G.update({"word_rnn.weight_ih_l0": gWih2, "word_rnn.weight_hh_l0": gWhh2, "word_rnn.bias_ih_l0": gb2, "word_rnn.bias_hh_l0": gb2b})
         sB.wait_event(ev_dout1)
         _ready("word_rnn")                                                      # (after the last readers of word_rnn's weights)
-        gE.zero_()
-        ops.embed_scatter_add_f32(gE, targets, 0, Lq - 1, B, Lq - 1, demb, E)
-        G["embedding.weight"] = gE
-        _ready("embedding")
     # ---- vid_rnn and feat_linear (the machine is free again): the chain dg1 -> d xproj -> feat_linear on one stream, vid_rnn's own
     # gradients on another
     gWih1 = _new("vid_rnn.weight_ih_l0", 4 * H, H)
