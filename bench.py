@@ -79,8 +79,11 @@ def synth_batch(B, seed, device=None, pinned=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md's clocks line).  nvidia-smi needs a few hundred
+    milliseconds to start and the timed region lasts tens of milliseconds, so the sampler is started before the warm-up, samples every
+    20 ms with nvidia-smi's own timestamps, and stop(t0, t1) keeps the samples that fall inside the timed window [t0, t1] (host
+    clock); if none does (a very short region), the samples within half a second of it are used and `window` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -89,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -99,30 +102,51 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        try:
+            self.t.join(timeout=1)
+        except Exception:
+            pass
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.lines:
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                rows.append((self._epoch(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[2:6]):
+        window = "all"
+        if t0 is not None and t1 is not None and rows and all(r[0] is not None for r in rows):
+            inside = [r for r in rows if t0 - 0.02 <= r[0] <= t1 + 0.02]
+            if inside:
+                rows, window = inside, "timed region"
+            else:
+                rows, window = [r for r in rows if t0 - 0.5 <= r[0] <= t1 + 0.5] or rows, "within 0.5 s of the timed region"
+        sm, mx, reasons = [r[1] for r in rows], [r[2] for r in rows], set()
+        for r in rows:
+            for nm, v in zip(names, r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------- reference arm / CPU baseline
@@ -224,14 +248,15 @@ def main():
         return trainer.step(f, t, m)
 
     # (with CUDA graphs: two eager steps, then one capture per rotating input buffer -- all of it before the timed region)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, n_rot + 2) if trainer.use_graph else args.warmup):
         step(i)
     sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = s2vt_b200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         loss = step(i)
@@ -239,7 +264,6 @@ def main():
     sync_all()
     ms_total = e0.elapsed_time(e1)
     launches = s2vt_b200.launch_count() - launches0
-    clocks = sampler.stop()
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -251,38 +275,50 @@ def main():
     # Next step's inputs are prefetched on a copy stream while this step computes (each copy is inside the timed region).
     host = [synth_batch(B, 4321 + rank * 100 + i, pinned=True) for i in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
-    dbuf = [(torch.empty_like(host[0][0], device=dev), torch.empty_like(host[0][1], device=dev)) for _ in range(2)]
     loss_host = torch.empty((), pin_memory=True)
 
-    def e2e_loop(n):
-        evs = [None, None]
+    def run_e2e(host):
+        dbuf = [(torch.empty_like(host[0][0], device=dev), torch.empty_like(host[0][1], device=dev)) for _ in range(2)]
 
-        def prefetch(i):
-            with torch.cuda.stream(copy_stream):
-                dbuf[i % 2][0].copy_(host[i % 2][0], non_blocking=True)
-                dbuf[i % 2][1].copy_(host[i % 2][1], non_blocking=True)
-                ev = torch.cuda.Event(); ev.record(copy_stream); evs[i % 2] = ev
-        prefetch(0)
-        for i in range(n):
-            torch.cuda.current_stream().wait_event(evs[i % 2])
-            if i + 1 < n:
-                copy_stream.wait_stream(torch.cuda.current_stream()) if i >= 1 else None
-                prefetch(i + 1)
-            l = trainer.step(dbuf[i % 2][0], dbuf[i % 2][1])
-            loss_host.copy_(l.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        def e2e_loop(n):
+            evs = [None, None]
 
-    e2e_loop(2)
-    sync_all()
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    sync_all()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (t2.item() / args.steps / 1e3)
-    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
+            def prefetch(i):
+                with torch.cuda.stream(copy_stream):
+                    dbuf[i % 2][0].copy_(host[i % 2][0], non_blocking=True)
+                    dbuf[i % 2][1].copy_(host[i % 2][1], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(copy_stream); evs[i % 2] = ev
+            prefetch(0)
+            for i in range(n):
+                torch.cuda.current_stream().wait_event(evs[i % 2])
+                if i + 1 < n:
+                    copy_stream.wait_stream(torch.cuda.current_stream()) if i >= 1 else None
+                    prefetch(i + 1)
+                l = trainer.step(dbuf[i % 2][0], dbuf[i % 2][1])
+                loss_host.copy_(l.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_loop(2)
+        sync_all()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        sync_all()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        return world * B / (t2.item() / args.steps / 1e3), host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * 8
+
+    e2e_value, h2d = run_e2e(host)
+    # the same loop fed from a pinned bf16 feature store (data.DeviceFeatureStore(dtype=bfloat16) semantics: features rounded once at
+    # load time to what the tensor-core path rounds them to at every step; identical loss and gradients) -- half the H2D bytes
+    e2e_bf16 = None
+    if precision == "bf16" and trainer.use_graph and trainer.max_graphs >= n_rot + 4:
+        host_bf = [(f.to(torch.bfloat16).pin_memory(), t, m) for f, t, m in host]
+        v, nb = run_e2e(host_bf)
+        e2e_bf16 = {"value": round(v, 2), "unit": "videos/s", "h2d_bytes_per_step": int(nb), "d2h_bytes_per_step": 4,
+                    "note": "features held as bf16 in pinned host memory (rounded once at load); `e2e` is the float32-input figure"}
+    clocks = sampler.stop(t_wall0, time.time())                # the window spans the timed regions (device-resident and end-to-end)
 
     # ---- per-kernel-family timing of one extra instrumented step (CUDA events on the launching stream)
     with ops.profile() as prof:
@@ -339,6 +375,7 @@ def main():
                    "launch": "CUDA graph replay of the whole step (one graph per input buffer)" if trainer.use_graph and trainer._graphs else "eager"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e_value, 2), "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "e2e_bf16_store": e2e_bf16,
         "roofline": roofline, "roofline_all": roofline_all, "kernels": kernels, "gemm_detail": gemm_detail,
         "step_tflops": round(world * B * FLOP_PER_VIDEO_TRAIN / (ms_step * 1e-3) / 1e12, 3), "loss": final_loss,
     }

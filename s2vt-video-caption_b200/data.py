@@ -18,7 +18,11 @@ import torch
 
 
 class DeviceFeatureStore:
-    def __init__(self, captions_file, feat_path, max_len: int = 80, mode: str = "train", device="cuda", feats_require_grad: bool = False):
+    def __init__(self, captions_file, feat_path, max_len: int = 80, mode: str = "train", device="cuda", feats_require_grad: bool = False,
+                 dtype: torch.dtype = torch.float32):
+        """dtype=torch.bfloat16: the features are rounded once, at load time, to what the tensor-core training path would round them to
+        at every step anyway (identical loss and gradients; half the memory, no per-step cast).  Only S2VT.forward_loss on the bf16
+        training path accepts such batches; decode and the exact path need float32."""
         with open(captions_file, encoding="utf-8") as f:
             data = json.load(f)
         self.word2ix: Dict[str, int] = data["word2ix"]
@@ -33,7 +37,11 @@ class DeviceFeatureStore:
         self.ids: List[str] = [p.stem for p in self.feat_paths]
         feats = [np.load(str(p)).astype(np.float32, copy=False) for p in self.feat_paths]
         host = torch.from_numpy(np.stack(feats)) if feats else torch.empty(0, max_len, 0)
-        self.feats = host.to(self.device)                      # [N, L, F] fp32, resident for the whole run
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("DeviceFeatureStore dtype must be float32 or bfloat16")
+        if dtype == torch.bfloat16 and feats_require_grad:
+            raise ValueError("bfloat16 features cannot require grad (feats.grad is a float32 quantity of the exact interface)")
+        self.feats = host.to(self.device).to(dtype)            # [N, L, F], resident for the whole run
 
     def __len__(self) -> int:
         return len(self.ids)

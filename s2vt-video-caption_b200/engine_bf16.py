@@ -432,7 +432,8 @@ def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, c
     T = 2 * Lq - 1
     dev = feats.device
     Bp = int(L.load().s2vt_lstm_bf16_batch_pad(B))
-    xb, _ = cast(feats, B * Lq, F)                                               # batch-major rows (b, l)
+    # batch-major rows (b, l), bf16: the features' own rounding -- a store that already holds them as bf16 hands them over as they are
+    xb = feats.view(B * Lq, F) if feats.dtype == BF else cast(feats, B * Lq, F)[0]
     xproj = torch.empty(Lq * B, H, dtype=BF, device=dev)                         # time-major rows (l, b)
     gemm(B * Lq, H, F, xb, F, False, S["feat_linear.weight"], F, False, xproj, rowmap(Lq, H, B * H), out_bf16=True,
          bias=P["feat_linear.bias"])

@@ -416,12 +416,14 @@ class S2VT(nn.Module):
         sd = dict(self.named_parameters())
         return {k: sd[k] for k in PARAM_ORDER}
 
-    def _check_inputs(self, feats: torch.Tensor):
+    def _check_inputs(self, feats: torch.Tensor, allow_bf16: bool = False):
         if feats.dim() != 3 or feats.shape[1] != self.length or feats.shape[2] != self.feat_dim:
             raise ValueError("feats must be [B, %d, %d] (got %s)" % (self.length, self.feat_dim, tuple(feats.shape)))
         require_cuda(feats, self.embedding.weight)
+        if feats.dtype == torch.bfloat16 and allow_bf16 and self._use_bf16() and not feats.requires_grad:
+            return                  # pre-rounded features (data.DeviceFeatureStore(dtype=bfloat16)): the tensor-core path skips its cast
         if feats.dtype != torch.float32:
-            raise ValueError("feats must be float32")
+            raise ValueError("feats must be float32 (bfloat16 only for forward_loss on the bf16 training path, without requires_grad)")
         if str(self.rnn_type).lower() != 'lstm':
             raise NotImplementedError("only rnn_type='lstm' is supported")
 
@@ -458,7 +460,7 @@ class S2VT(nn.Module):
         criterion(model(feats, targets[:, :-1], 'train'), targets, mask) (train.py:120-122) without
         materialising [B,L-1,V] logits for autograd.  `mask` is accepted for signature parity; the
         reference's criterion is independent of it (utils.py:19-26)."""
-        self._check_inputs(feats)
+        self._check_inputs(feats, allow_bf16=True)
         if targets.dim() != 2 or targets.shape[1] != self.length:
             raise RuntimeError("targets must be [B, length] (got %s)" % (tuple(targets.shape),))
         P = self._params()

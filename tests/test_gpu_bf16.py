@@ -448,3 +448,29 @@ def test_bucketwise_adam_matches_whole_buffer_step(dev, precision):
     for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
         # identical kernels; only the atomic accumulation order of split-K / scatter-add partial sums may differ
         assert (a - b).abs().max().item() <= 2e-5 * max(1e-3, b.abs().max().item()), k
+
+
+def test_bf16_feature_store_batches_match_float32_batches(dev):
+    """Features handed over as bfloat16 (data.DeviceFeatureStore(dtype=bfloat16): rounded once at load time) give the loss and gradients
+    of the float32 features: the tensor-core path's first act on float32 features is that very rounding.  Decode and requires_grad
+    inputs still insist on float32."""
+    V, F, H, E, Lq, B = 520, 64, 128, 64, 10, 24
+    g = torch.Generator().manual_seed(23)
+    feats = torch.randn(B, Lq, F, generator=g).to(dev)
+    targets = torch.randint(0, V, (B, Lq), generator=g).to(dev)
+    torch.manual_seed(4)
+    model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    out = []
+    for x in (feats, feats.to(torch.bfloat16)):
+        model.zero_grad(set_to_none=True)
+        loss = model.forward_loss(x, targets)
+        loss.backward()
+        out.append((loss.item(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}))
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+    for k in out[0][1]:
+        a, b = out[1][1][k].double(), out[0][1][k].double()
+        assert (a - b).norm().item() <= 1e-5 * max(1e-30, b.norm().item()), k     # (split-K / atomic summation order only)
+    with pytest.raises(ValueError):
+        model(feats.to(torch.bfloat16), mode="test")
+    with pytest.raises(ValueError):
+        model.forward_loss(feats.to(torch.bfloat16).requires_grad_(True), targets)
