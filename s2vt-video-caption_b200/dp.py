@@ -5,7 +5,8 @@ across ranks, and ONE exchange step -- a bucketed all-reduce (average) of the fl
 The reference has no distributed code; because its loss is a mean over B*(L-1) positions and
 every rank sees the same B, averaging rank gradients equals the single-process gradient of the concatenated batch.
 
-Bucket order = order in which backward finishes them: out_linear -> word_rnn -> embedding -> vid_rnn -> feat_linear.
+Buckets, in the order the exact path finishes them: out_linear (weight) -> word_rnn -> embedding (+ out_linear.bias) -> vid_rnn ->
+feat_linear; the tensor-core path releases the embedding bucket before word_rnn.  Every rank runs the same code, hence the same order.
 """
 from __future__ import annotations
 
@@ -16,9 +17,11 @@ import torch
 import torch.distributed as dist
 
 BUCKETS: Tuple[Tuple[str, Tuple[str, ...]], ...] = (
-    ("out_linear", ("out_linear.weight", "out_linear.bias")),
+    # out_linear's bias (a column sum over the 131 MB of dlogits) travels with the embedding table it is adjacent to in the flat
+    # buffer: the first all-reduce, 26.6 MB, then starts right behind the weight-gradient product instead of one more pass later
+    ("out_linear", ("out_linear.weight",)),
     ("word_rnn", ("word_rnn.weight_ih_l0", "word_rnn.weight_hh_l0", "word_rnn.bias_ih_l0", "word_rnn.bias_hh_l0")),
-    ("embedding", ("embedding.weight",)),
+    ("embedding", ("out_linear.bias", "embedding.weight")),
     ("vid_rnn", ("vid_rnn.weight_ih_l0", "vid_rnn.weight_hh_l0", "vid_rnn.bias_ih_l0", "vid_rnn.bias_hh_l0")),
     ("feat_linear", ("feat_linear.weight", "feat_linear.bias")),
 )
@@ -72,7 +75,12 @@ class GradAllReducer:
             ev.record(torch.cuda.current_stream(self.flat.device))
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
+                from . import ops
+                if ops.MARKS is not None:                                          # tools/timeline_step.py
+                    ops._mark("B all_reduce[%s %.1f MB]" % (bucket, view.numel() * 4 / 1e6))
                 dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)      # NCCL averages in the collective
+                if ops.MARKS is not None:
+                    ops._mark("E all_reduce[%s %.1f MB]" % (bucket, view.numel() * 4 / 1e6))
         else:
             if self.cuda:
                 dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)

@@ -532,10 +532,9 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gW = _new("out_linear.weight", V, H)
     gb = _new("out_linear.bias", V)
     with beside_sweeps(capped):
-        colsum_bf16(dl_bf, R, V, V, gb)            # (first: behind the product's thousands of queued CTAs it would hold the bucket back)
         gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True, bulk=capped)
-        G["out_linear.weight"], G["out_linear.bias"] = gW, gb
-        _ready("out_linear")
+        G["out_linear.weight"] = gW
+        _ready("out_linear")                        # (the bias gradient belongs to the embedding bucket, dp.BUCKETS)
     # ---- word_rnn weight / bias / embedding gradients (beside the vid_rnn sweep)
     gWih2 = _new("word_rnn.weight_ih_l0", 4 * H, E + H)
     gWhh2 = _new("word_rnn.weight_hh_l0", 4 * H, H)
@@ -544,6 +543,9 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     demb = torch.empty(R, E, device=dev)
     with torch.cuda.stream(sB):
         sB.wait_event(ev_bulk)
+        with beside_sweeps(capped):
+            colsum_bf16(dl_bf, R, V, V, gb)
+        G["out_linear.bias"] = gb
         sB.wait_event(ev_dg2)
         with beside_sweeps(capped):
             # embedding first: its bucket is one of the two big ones (V x E), and in a data-parallel run its all-reduce should start early

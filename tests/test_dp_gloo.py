@@ -73,7 +73,7 @@ def test_bucketed_allreduce_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     names, offsets, sizes, n = _layout()
-    assert all(b == 2 * 4 * sum(sizes) for _, _, b in res)    # every parameter byte reduced once per round
+    assert all(2 * 4 * sum(sizes) <= b <= 2 * 4 * n for _, _, b in res)    # every parameter byte reduced once per round (+ alignment padding inside a bucket)
 
 
 def test_bucket_ranges_cover_all_parameters_once():

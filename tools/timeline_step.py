@@ -28,7 +28,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     args = ap.parse_args()
     C = bench.CFG
-    dev = torch.device("cuda", 0)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:                                   # under torchrun: the data-parallel step (rank 0 prints)
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_MIN_CTAS", "16")
+        dist.init_process_group("nccl", device_id=dev)
+        if rank != 0:
+            sys.stdout = open(os.devnull, "w")
     torch.manual_seed(0)
     model = s2vt_b200.S2VT(C["V"], C["F"], C["L"], dim_hid=C["H"], dim_embed=C["E"], train_precision="bf16").to(dev)
     opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-4)
@@ -93,3 +101,9 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
