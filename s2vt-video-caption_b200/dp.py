@@ -121,7 +121,8 @@ class DataParallelTrainer:
         # (Adam's step count / lr live on the device).  S2VT_CUDA_GRAPH=0 or cuda_graph=False keeps every step eager.
         if cuda_graph is None:
             cuda_graph = os.environ.get("S2VT_CUDA_GRAPH", "1") != "0"
-        self.use_graph = bool(cuda_graph) and f["g"].is_cuda
+        from . import ops
+        self.use_graph = bool(cuda_graph) and f["g"].is_cuda and not ops.serialising_profiler_attached()
         self._graphs: Dict[tuple, tuple] = {}
         self._eager_steps = 0
         self._pool = None

@@ -349,9 +349,9 @@ def _run_coupled(key, trailing_sweep, products):
     """Enqueue a trailing sweep (which spins on device flags) and the products that raise those flags.  Normally the sweep goes first, so
     that it is resident before its first chunk is ready.  The first time a configuration runs, the products go first and the sweep
     starts behind them: the CUDA runtime loads a kernel's code on its first launch and may have to wait for the device to drain to do
-    so -- with a spinning kernel resident that would never happen.  (S2VT_WAVEFRONT=safe keeps this order: profilers that serialise
-    kernels need it.)"""
-    if key in _WARM and _os.environ.get("S2VT_WAVEFRONT") != "safe":
+    so -- with a spinning kernel resident that would never happen.  (S2VT_WAVEFRONT=safe, or a detected Nsight Compute, keeps this
+    order: profilers that serialise kernels need it.)"""
+    if key in _WARM and _os.environ.get("S2VT_WAVEFRONT") != "safe" and not ops.serialising_profiler_attached():
         trailing_sweep(False)
         products()
     else:

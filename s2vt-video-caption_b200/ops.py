@@ -43,6 +43,14 @@ class profile:
         return out
 
 
+def serialising_profiler_attached() -> bool:
+    """True under Nsight Compute, which replays kernels one at a time: kernels that wait for each other on the device (the wave front)
+    must then be enqueued in dependency order, and must not sit in one CUDA graph (S2VT_WAVEFRONT=safe, eager steps)."""
+    import os
+    inj = os.environ.get("CUDA_INJECTION64_PATH", "").lower()
+    return "NV_COMPUTE_PROFILER_PERFWORKS_DIR" in os.environ or "nsight-compute" in inj or "libcuda-injection" in inj
+
+
 MARKS = None             # tools/timeline_step.py: dict(buf=int64 device tensor, names=[...]) -> %globaltimer stamps around every call
 
 

@@ -100,3 +100,23 @@ def test_load_glove_weights(tmp_path):
     assert m.embedding.weight[5].tolist() == [1, 2, 3, 4] and m.embedding.weight[6].tolist() == [5, 6, 7, 8]
     assert m.embedding.weight.requires_grad and m.embedding.weight[7].abs().sum() > 0          # xavier-normal row, still trainable
     assert list(m.state_dict().keys())[-1] == "embedding.weight"
+
+
+def test_wavefront_chunk_boundaries_are_valid_for_every_length():
+    """engine_bf16._time_bounds: strictly increasing from 0 to T = 2L - 1, step L is always a boundary (the embedding half of word_rnn's
+    input starts there), at most S2VT_MAX_SYNC chunks -- forwards and for BPTT, for every caption length the wave front accepts."""
+    from s2vt_b200 import engine_bf16 as EB
+    for Lq in range(16, 400):
+        T = 2 * Lq - 1
+        for backward in (False, True):
+            b = EB._time_bounds(Lq, T, backward)
+            assert b[0] == 0 and b[-1] == T and Lq in b
+            assert all(x < y for x, y in zip(b, b[1:]))
+            assert len(b) - 1 <= EB.MAX_SYNC
+
+
+def test_max_sync_matches_header():
+    import re
+    from s2vt_b200 import engine_bf16 as EB
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "s2vt_b200.h")).read()
+    assert int(re.search(r"#define\s+S2VT_MAX_SYNC\s+(\d+)", hdr).group(1)) == EB.MAX_SYNC
