@@ -221,6 +221,10 @@ def main():
         if not os.environ.get("S2VT_KEEP_NCCL_DEBUG"):
             os.environ.pop("NCCL_DEBUG", None)        # NCCL's version banner goes to stdout; rank 0 must print ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
+    numa_node = None
+    if world > 1 and os.environ.get("S2VT_NUMA_BIND", "1") != "0":
+        from s2vt_b200.dp import bind_to_local_numa
+        numa_node = bind_to_local_numa(local_rank)          # before any pinned host buffer exists (end-to-end loop feeds from them)
     s2vt_b200.load()
     peaks = load_peaks()
     B = args.batch
@@ -372,7 +376,8 @@ def main():
                                "padded to 80, V=13000, H=E=512, random init" % B,
                    "global_batch": world * B, "parallelism": "dp%d" % world, "precision": precision,
                    "l2_policy": "inputs rotate over 4 device-resident batches (336 MB > 126 MB L2)",
-                   "launch": "CUDA graph replay of the whole step (one graph per input buffer)" if trainer.use_graph and trainer._graphs else "eager"},
+                   "launch": "CUDA graph replay of the whole step (one graph per input buffer)" if trainer.use_graph and trainer._graphs else "eager",
+                   "host_numa_node_rank0": numa_node},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e_value, 2), "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
         "e2e_bf16_store": e2e_bf16,
