@@ -359,6 +359,13 @@ def main():
                 # a chain of T = 159 dependent steps: what bounds it is the latency of one step (tensor-memory MMA -> activations -> DSMEM
                 # exchange across the 16-CTA cluster); the tensor fraction is reported for information
                 base["us_per_timestep"] = round(base["us_per_launch"] / (2 * CFG["L"] - 1), 3)
+                # on-chip traffic of one step, all clusters of the sweep: every CTA's MMAs read its 4H/CS x H bf16 weight slice (tensor
+                # memory) and the 16-column h / dgates operand (shared memory); the exchange moves B x H bf16 through distributed
+                # shared memory to each of the CS = H/32 CTAs of a cluster
+                H_, B_ = CFG["H"], B
+                step_s = base["us_per_timestep"] * 1e-6
+                base["onchip_operand_gbs"] = round((4 * H_ * H_ * 2 * ((B_ + 15) // 16) + B_ * H_ * 2 * (H_ // 32)) / step_s / 1e9, 1)
+                base["dsmem_exchange_gbs"] = round(B_ * H_ * 2 * (H_ // 32) / step_s / 1e9, 1)
                 base["note"] = ("serial recurrence (159 dependent steps, north-star target < 5 us/step at batch 64); two sweeps run side by "
                                 "side as a wave front, so a launch's duration includes the trailing sweep's wait for the leading one")
         else:

@@ -236,16 +236,25 @@ BWD_SERVER_CTAS = int(_os.environ.get("S2VT_BWD_SERVER_CTAS", "20"))
 
 def _time_bounds(Lq: int, T: int, backward: bool = False):
     """Chunk boundaries of the wave front.  The trailing sweep can never be ahead of the leading one by less than a chunk plus its
-    coupling product, at the start and at the end of the sequence alike, so chunks are short (S2VT_WAVE_CHUNK steps, default 10; the
-    very first one half of that) -- limited by the product's efficiency at few rows and by MAX_SYNC.  No chunk straddles step L (the
-    embedding half of word_rnn's input starts there).  For BPTT the same pattern is laid out from the end of the sequence."""
+    coupling tiles, at the start and at the end of the sequence alike, so chunks are short (S2VT_WAVE_CHUNK steps, default 10) and
+    shorter still at both ends (3 steps to get the trailing sweep going, 4-step chunks over the last 12 steps: that is the lag with which
+    it finishes) -- limited by what a chunk boundary costs the leading sweep (a fence and a barrier) and by MAX_SYNC.  No chunk
+    straddles step L (the embedding half of word_rnn's input starts there).  For BPTT the same pattern is laid out from the end of the
+    sequence."""
     c = max(2, int(_os.environ.get("S2VT_WAVE_CHUNK", "10")))
-    c = max(c, -(-T // (MAX_SYNC - 2)))
-    pos, p = [0], c // 2 + 1
-    while p < T:
+    c = max(c, -(-T // (MAX_SYNC - 8)))
+    taper = _os.environ.get("S2VT_WAVE_TAPER", "1") != "0" and T >= 4 * c
+    pos = [0] + ([3] if taper and c >= 6 else [])
+    p = c // 2 + 1
+    end = T - 12 if taper else T
+    while p < end:
         pos.append(p)
         p += c
-    if T - pos[-1] < c // 2 and len(pos) > 1:
+    if taper:
+        if end - pos[-1] < 3:
+            pos.pop()
+        pos += [T - 12, T - 8, T - 4]
+    elif T - pos[-1] < c // 2 and len(pos) > 1:
         pos.pop()
     pos.append(T)
     cut = (T - Lq) if backward else Lq                       # position of step L in processing order
