@@ -18,8 +18,10 @@ from . import ops
 from .lib import dense, rowmap
 
 BF = torch.bfloat16
-# SM budget of the work that runs beside the two resident BPTT sweeps (96 of 148 SMs at B = 64): persistent GEMM CTAs (one per SM) and
-# CTAs of the memory-bound kernels (they share SMs with GEMM CTAs).  What is left over serves the wave front's coupling products.
+# SM budgets for work launched beside two resident sweeps (96 of 148 SMs at B = 64) that must leave room for a kernel launched after it:
+# persistent GEMM CTAs (one per SM; used for the embedding half of word_rnn's input product, which runs beside the forward coupling
+# kernel) and CTAs of the memory-bound kernels.  With the resident coupling kernel (WAVE_SERVER, the default) the backward's gradient
+# products need no budget; the per-chunk coupling path (S2VT_WAVE_SERVER=0) caps them all.
 BULK_CTAS = int(_os.environ.get("S2VT_BULK_CTAS", "28"))
 BULK_ELT_CTAS = int(_os.environ.get("S2VT_BULK_ELT_CTAS", "104"))
 
