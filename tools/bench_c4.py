@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3]: S2VT at the paper's sizing (ResNet152 2048-d features, hidden 1000, embedding 500 = the constructor
+default, S2VTModel.py:11), batch 256 per GPU, one train step = forward_loss + backward + FusedAdam.  H = 1000 is outside the cluster
+recurrence's range (H % 128 == 0, H <= 512), so this runs on the exact fp32 path.  Prints one JSON line.
+
+    python tools/bench_c4.py [--steps 5] [--batch 256]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+import s2vt_b200
+from s2vt_b200.dp import DataParallelTrainer
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=256)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    V, F, L, H, E, B = 13000, 2048, 80, 1000, 500, args.batch
+    torch.manual_seed(0)
+    model = s2vt_b200.S2VT(V, F, L, dim_hid=H, dim_embed=E).to(dev)
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-4)
+    trainer = DataParallelTrainer(model, opt)
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(B, L, F, generator=g).to(dev)
+    targets = torch.zeros(B, L, dtype=torch.int64)
+    targets[:, 0] = 3
+    targets[:, 1:27] = torch.randint(5, V, (B, 26), generator=g)
+    targets[:, 27] = 4
+    targets = targets.to(dev)
+    for _ in range(args.warmup):
+        trainer.step(feats, targets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(feats, targets)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"metric": "S2VT train videos/sec, paper sizing (configs[3])", "value": round(B / (ms / 1e3), 1), "ms_per_step": round(ms, 2),
+                      "n_gpus": 1, "precision": "fp32 exact (H = 1000 is outside the tensor-core recurrence's range)", "batch_per_gpu": B,
+                      "dims": {"V": V, "F": F, "L": L, "H": H, "E": E}, "loss": float(loss.item()),
+                      "device_error_flag": int(s2vt_b200.load().s2vt_device_error_flag(None))}))
+
+
+if __name__ == "__main__":
+    main()
