@@ -120,3 +120,33 @@ def test_max_sync_matches_header():
     from s2vt_b200 import engine_bf16 as EB
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "s2vt_b200.h")).read()
     assert int(re.search(r"#define\s+S2VT_MAX_SYNC\s+(\d+)", hdr).group(1)) == EB.MAX_SYNC
+
+
+def test_feature_store_bf16_holds_the_rounded_features(tiny_dataset):
+    cf, fd, data = tiny_dataset
+    st32 = s2vt_b200.DeviceFeatureStore(cf, fd, max_len=6, mode="train", device="cpu")
+    st16 = s2vt_b200.DeviceFeatureStore(cf, fd, max_len=6, mode="train", device="cpu", dtype=torch.bfloat16)
+    assert st16.feats.dtype == torch.bfloat16 and st16.ids == st32.ids
+    assert torch.equal(st16.feats, st32.feats.to(torch.bfloat16))            # round-to-nearest-even, once, at load time
+    np.random.seed(1)
+    f16 = st16.batch([1, 3])[0]
+    assert f16.dtype == torch.bfloat16 and torch.equal(f16, st32.feats[[1, 3]].to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        s2vt_b200.DeviceFeatureStore(cf, fd, max_len=6, mode="train", device="cpu", dtype=torch.float16)
+    with pytest.raises(ValueError):
+        s2vt_b200.DeviceFeatureStore(cf, fd, max_len=6, mode="train", device="cpu", dtype=torch.bfloat16, feats_require_grad=True)
+
+
+def test_profiler_detection_and_numa_binding_degrade_gracefully(monkeypatch):
+    from s2vt_b200 import dp, ops
+    for k in ("NV_COMPUTE_PROFILER_PERFWORKS_DIR", "CUDA_INJECTION64_PATH"):
+        monkeypatch.delenv(k, raising=False)
+    assert not ops.serialising_profiler_attached()
+    monkeypatch.setenv("CUDA_INJECTION64_PATH", "/opt/nvidia/nsight-compute/2025.2.1/target/linux-desktop-glibc_2_11_3-x64/libcuda-injection.so")
+    assert ops.serialising_profiler_attached()
+    monkeypatch.setenv("CUDA_INJECTION64_PATH", "/opt/nsys/libToolsInjection64.so")        # a tracer, not a serialising profiler
+    assert not ops.serialising_profiler_attached()
+    before = os.sched_getaffinity(0)
+    assert dp.bind_to_local_numa(0) is None or isinstance(dp.bind_to_local_numa(0), int)  # no GPU / no topology: None, never raises
+    assert os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
