@@ -185,8 +185,10 @@ class DataParallelTrainer:
             with torch.cuda.stream(self._adam_stream):
                 self._adam_stream.wait_event(ev)
                 self.opt.step_range(a, b)
+                self.opt.refresh_derived(bucket)
         else:
             self.opt.step_range(a, b)
+            self.opt.refresh_derived(bucket)
 
     def _step_eager(self, feats, targets, mask=None):
         self.opt.zero_grad(set_to_none=True)
@@ -206,7 +208,14 @@ class DataParallelTrainer:
         if not (self.use_graph and feats.is_cuda and self.model._use_bf16()) or ops._PROFILE is not None:
             self._eager_steps += 1
             return self._step_eager(feats, targets, mask)
-        key = (feats.data_ptr(), targets.data_ptr(), tuple(feats.shape), tuple(targets.shape), feats.requires_grad)
+        # A captured step reads the optimizer's bf16 weight shadows (and the derived W_hh^T / bias sums) as the previous step left them.
+        # If anything else touched the weights since (load_state_dict, an in-place edit, another optimizer), run this step eagerly: it
+        # re-derives them from the fp32 masters and leaves everything current again.
+        f = self.opt._flat
+        if f.get("shadow_state") != (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"])) or not f.get("derived_ok"):
+            self._eager_steps += 1
+            return self._step_eager(feats, targets, mask)
+        key = (feats.data_ptr(), targets.data_ptr(), tuple(feats.shape), tuple(targets.shape), feats.requires_grad, feats.dtype)
         ent = self._graphs.get(key)
         if ent is None:
             if self._eager_steps < 2 or len(self._graphs) >= self.max_graphs:

@@ -172,11 +172,13 @@ class ShadowCache:
         for name in ("vid_rnn.weight_hh_l0", "word_rnn.weight_hh_l0"):
             w = P[name]
             if fused is not None:
-                t[name], t[name + ".T"] = fused[name], cast(w, w.shape[0], w.shape[1], want_t=True, want_plain=False)[1]
+                t[name] = fused[name]
+                t[name + ".T"] = fused[name + ".T"] if name + ".T" in fused else cast(w, w.shape[0], w.shape[1], want_t=True, want_plain=False)[1]
             else:
                 t[name], t[name + ".T"] = cast(w, w.shape[0], w.shape[1], want_t=True)
-        t["b1"] = ops.add_f32(P["vid_rnn.bias_ih_l0"], P["vid_rnn.bias_hh_l0"], torch.empty_like(P["vid_rnn.bias_ih_l0"]))
-        t["b2"] = ops.add_f32(P["word_rnn.bias_ih_l0"], P["word_rnn.bias_hh_l0"], torch.empty_like(P["word_rnn.bias_ih_l0"]))
+        for kb, layer in (("b1", "vid_rnn"), ("b2", "word_rnn")):            # (FusedAdam.refresh_derived keeps these current too)
+            t[kb] = fused[kb] if fused is not None and kb in fused else \
+                ops.add_f32(P[layer + ".bias_ih_l0"], P[layer + ".bias_hh_l0"], torch.empty_like(P[layer + ".bias_ih_l0"]))
         self.key, self.t = key, t
         return t
 

@@ -70,6 +70,7 @@ class FusedAdam(torch.optim.Optimizer):
         model._grad_views = dict(zip(names, views))
         model._on_bucket_ready = on_bucket_ready
         model._adam_shadow = self            # engine_bf16.ShadowCache asks shadow_views() for weights the last step() already cast
+        f["names"] = names
 
     def shadow_views(self, named_params):
         """{name: bf16 view} of the weights as written by the last Adam kernel, or None when they are stale (no step yet, another
@@ -84,7 +85,10 @@ class FusedAdam(torch.optim.Optimizer):
         base = f["p"].data_ptr()
         if versions != tuple(p._version for p in params) or any(p.data_ptr() != base + o * 4 for p, o in zip(params, f["offsets"])):
             return None
-        return {n: f["shadow"][o:o + p.numel()].view(p.shape) for (n, p), o in zip(named_params, f["offsets"])}
+        views = {n: f["shadow"][o:o + p.numel()].view(p.shape) for (n, p), o in zip(named_params, f["offsets"])}
+        if f.get("derived_ok"):
+            views.update(f["derived"])      # W_hh^T (bf16) and b_ih + b_hh of both LSTMs, refreshed right behind their buckets' updates
+        return views
 
     # ---- bucket-wise stepping: Adam on a slice of the flat buffer as soon as that slice's gradient is final, so that most of
     # the (HBM-bound) update runs beside the BPTT sweeps instead of after them.  begin_step() / step_range()* / finish_step().
@@ -106,6 +110,27 @@ class FusedAdam(torch.optim.Optimizer):
                 self.sync_lr()
             group = self.param_groups[0]
             ops.adam_prepare(f["step_dev"], f["lr_dev"], float(group["betas"][0]), float(group["betas"][1]), f["hyper_dev"])
+
+    @torch.no_grad()
+    def refresh_derived(self, bucket: str) -> None:
+        """Right behind the Adam update of an LSTM's bucket (same stream): what the tensor-core path derives from its weights -- the
+        transposed bf16 W_hh for the BPTT kernel and b_ih + b_hh -- is rebuilt into persistent buffers, in the tail of THIS step
+        instead of at the head of the next one (where it sits on the serial chain).  In place is safe for the reason it is for the
+        bf16 shadows: the bucket is released only after the last reader of its weights."""
+        f = self._flat
+        if f is None or "step_dev" not in f or "names" not in f or bucket not in ("vid_rnn", "word_rnn"):
+            return
+        from . import lib as L
+        P = dict(zip(f["names"], f["params"]))
+        w = P[bucket + ".weight_hh_l0"]
+        d = f.setdefault("derived", {})
+        kt, kb = bucket + ".weight_hh_l0.T", ("b1" if bucket == "vid_rnn" else "b2")
+        if kt not in d:
+            d[kt] = torch.empty(w.shape[1], w.shape[0], dtype=torch.bfloat16, device=w.device)
+            d[kb] = torch.empty_like(P[bucket + ".bias_ih_l0"])
+        L.check(L.load().s2vt_cast_bf16(L.stream_ptr(w.device), L.ptr(w), None, L.ptr(d[kt]), w.shape[0], w.shape[1]), "s2vt_cast_bf16")
+        ops.add_f32(P[bucket + ".bias_ih_l0"], P[bucket + ".bias_hh_l0"], d[kb])
+        f.setdefault("derived_done", set()).add(bucket)
 
     def note_replayed_step(self) -> None:
         """Host-side bookkeeping for one replay of a captured train step (the device did begin_step .. finish_step itself)."""
@@ -138,6 +163,7 @@ class FusedAdam(torch.optim.Optimizer):
             pos = max(pos, b)
         f["stepped"] = []
         f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))
+        f["derived_ok"] = f.pop("derived_done", set()) == {"vid_rnn", "word_rnn"}     # (a replayed graph repeats what its capture did)
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -159,4 +185,5 @@ class FusedAdam(torch.optim.Optimizer):
         ops.adam_f32(f["p"], f["g"], f["m"], f["v"], float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]),
                      float(group["eps"]), f["step"], grad_scale=grad_scale, bf16_copy=f["shadow"])
         f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))
+        f["derived_ok"] = False
         return loss
