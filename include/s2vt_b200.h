@@ -324,6 +324,41 @@ int s2vt_vocab_ce_fwd_bf16(void* stream, int R, int V, int K, const void* A_bf16
 int s2vt_ce_dlogits_inplace_bf16(void* stream, void* logits_bf16, int64_t R, int V, int64_t ld, const float* row_lse,
                                  const int64_t* targets, s2vt_rowmap tmap, const float* gscale);
 
+/* ------------------------------------------------------------------ exact-grade decode on the tensor cores ("x" path)
+ * fp32 operands are scaled by a power of two and split into two fp16 planes (hi, lo); a product is three
+ * tcgen05.mma.kind::f16 passes (hi*lo + lo*hi + hi*hi) into one fp32 TMEM accumulator: per-term error <= 2^-21, below what an
+ * fp32 FMA chain accumulates over K >= 512 terms (csrc/xdec_sm100.cu has the derivation, tests/test_gpu_xdec.py measures it). */
+typedef struct s2vt_xdec_cfg {
+  int32_t vocab_size, feat_dim, length, dim_hid, dim_embed, sos_ix, eos_ix;
+} s2vt_xdec_cfg;
+
+/* C[cmap(m), n] = sum_k A[m*lda + k] B[n*ldb + k] (+ bias[n]) (+ C): fp32 in, fp32 out, split on the fly.
+ * ws >= s2vt_xgemm_ws_bytes(M,N,K).  replaces: nn.Linear / addmm (S2VTModel.py:54,80) at fp32-grade accuracy. */
+int64_t s2vt_xgemm_ws_bytes(int M, int N, int K);
+int s2vt_xgemm_f32(void* stream, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                   float* C, s2vt_rowmap cmap, const float* bias, int accumulate, void* ws);
+
+/* Weight preparation for the decode entry points: fp16 (hi, lo) planes of the 13 state_dict tensors (gate rows interleaved,
+ * dimensions padded to multiples of 8) and the table EW = embedding . W_ih(word_rnn)[:, :E]^T  [V, 4H].
+ *   params: 13 device pointers in state_dict registration order (S2VTModel.py:19-28)
+ *   wbuf >= s2vt_xdec_weights_bytes(cfg): caller-owned, valid until the weights change. */
+int64_t s2vt_xdec_weights_bytes(s2vt_xdec_cfg cfg);
+int s2vt_xdec_prepare(void* stream, s2vt_xdec_cfg cfg, const float* const* params, void* wbuf);
+
+/* S2VT.forward(mode='test'), S2VTModel.py:82-110: feats [B, L, F] f32 -> tokens [B, L-1] i64 (batch-major).
+ * feat_linear, both LSTMs (159 + 80 steps), 79 x (word_rnn step, out_linear, argmax); the [B,V] logits are never stored.
+ * Work is enqueued on `stream` and on one internal side stream joined back into `stream` before returning. */
+int64_t s2vt_xdec_greedy_ws_bytes(s2vt_xdec_cfg cfg, int B);
+int s2vt_xdec_greedy(void* stream, s2vt_xdec_cfg cfg, const void* wbuf, int B, const float* feats, int64_t* tokens, void* ws);
+
+/* S2VT.forward(mode='beam_search'), S2VTModel.py:56-61,149-240, lock-step over videos x beams (same outputs as
+ * s2vt_beam_search_f32).  beam_width <= 8.  check_every > 0: the host reads the number of finished videos every that many
+ * depths (one stream sync each) and stops early when all are; host_flag: pinned int32 for that read (may be NULL if 0). */
+int64_t s2vt_xdec_beam_ws_bytes(s2vt_xdec_cfg cfg, int B, int beam_width, int max_depth);
+int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf, int B, const float* feats, int beam_width, int max_depth,
+                   int topk, const float* len_pen, int64_t* out_tokens, int32_t* out_len, void* ws, int check_every,
+                   int32_t* host_flag);
+
 #ifdef __cplusplus
 }
 #endif

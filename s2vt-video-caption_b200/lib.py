@@ -27,6 +27,11 @@ def dense(ld: int) -> RowMap:
     return RowMap(1, int(ld), 0)
 
 
+class XdecCfg(C.Structure):
+    """s2vt_xdec_cfg (include/s2vt_b200.h)"""
+    _fields_ = [(n, C.c_int32) for n in ("vocab_size", "feat_dim", "length", "dim_hid", "dim_embed", "sos_ix", "eos_ix")]
+
+
 _vp, _i, _i64, _f, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 
 # name -> (restype, argtypes); kept in one table so tests can compare it with the header
@@ -83,6 +88,14 @@ SIGNATURES = {
     "s2vt_beam_ws_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
     "s2vt_beam_search_f32": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp]),
+    "s2vt_xgemm_ws_bytes": (_i64, [_i, _i, _i]),
+    "s2vt_xgemm_f32": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, RowMap, _vp, _i, _vp]),
+    "s2vt_xdec_weights_bytes": (_i64, [XdecCfg]),
+    "s2vt_xdec_prepare": (_i, [_vp, XdecCfg, _vp, _vp]),
+    "s2vt_xdec_greedy_ws_bytes": (_i64, [XdecCfg, _i]),
+    "s2vt_xdec_greedy": (_i, [_vp, XdecCfg, _vp, _i, _vp, _vp, _vp]),
+    "s2vt_xdec_beam_ws_bytes": (_i64, [XdecCfg, _i, _i, _i]),
+    "s2vt_xdec_beam": (_i, [_vp, XdecCfg, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

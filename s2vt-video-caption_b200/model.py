@@ -361,7 +361,7 @@ class _TrainLogitsBf16Fn(torch.autograd.Function):
 class S2VT(nn.Module):
     def __init__(self, vocab_size, feat_dim, length, dim_hid=500, dim_embed=500, feat_dropout=0, rnn_dropout=0,
                  out_dropout=0, num_layers=1, bidirectional=False, rnn_type='lstm', sos_ix=3, eos_ix=4,
-                 train_precision: str = "auto", decode_precision: str = "fp32"):
+                 train_precision: str = "auto", decode_precision: str = "x"):
         super().__init__()
         if str(rnn_type).lower() != 'lstm':
             raise NotImplementedError("only rnn_type='lstm' is supported (the reference warns against GRU, train.py:35)")
@@ -390,11 +390,36 @@ class S2VT(nn.Module):
         self._on_bucket_ready = None
         self._adam_shadow = None                # set by FusedAdam.attach(): its kernel keeps bf16 copies of the weights current
         self._shadow = EB.ShadowCache()         # bf16 mirrors of the weights (derived, rebuilt lazily, never saved)
+        self._xdec = None                       # (key, cfg, weight planes, workspace) of the tensor-core decode path
+        self.beam_check_every = 6               # beam search: host looks for "every video finished" this often (0 = never)
 
     def __getstate__(self):
         st = self.__dict__.copy()               # whole-module pickles (train.py:167) carry parameters only
         st["_grad_views"], st["_on_bucket_ready"], st["_adam_shadow"], st["_shadow"] = None, None, None, EB.ShadowCache()
+        st["_xdec"] = None
         return st
+
+    def __setstate__(self, st):
+        st.setdefault("_xdec", None)
+        st.setdefault("beam_check_every", 6)
+        self.__dict__.update(st)
+
+    # ---- tensor-core decode path ("x": fp32 operands as fp16 hi/lo planes, csrc/xdec_sm100.cu)
+    def _use_xdec(self, beam_width=None) -> bool:
+        if self.decode_precision == "fp32":
+            return False
+        if self.decode_precision != "x":
+            raise ValueError("decode_precision must be 'x' (tcgen05, fp32-grade) or 'fp32' (CUDA-core FMA)")
+        return beam_width is None or beam_width <= 8        # wider beams than the fused top-k keeps: FMA path
+
+    def _xdec_state(self):
+        P = self._params()
+        key = (ops.WEIGHT_EPOCH, int(self.sos_ix), int(self.eos_ix)) + tuple((p.data_ptr(), p._version) for p in P.values())
+        if self._xdec is None or self._xdec["key"] != key:
+            cfg = ops.xdec_cfg(self.vocab_size, self.feat_dim, self.length, self.dim_hid, self.dim_embed, self.sos_ix, self.eos_ix)
+            wbuf = ops.xdec_prepare(cfg, [P[k].detach() for k in PARAM_ORDER])
+            self._xdec = dict(key=key, cfg=cfg, wbuf=wbuf, ws=None, flag=None, pen={})
+        return self._xdec
 
     def _use_bf16(self) -> bool:
         """train_precision: 'bf16' = tensor cores (raises if the shapes are unsupported), 'fp32' = exact CUDA-core path,
@@ -497,8 +522,13 @@ class S2VT(nn.Module):
 
     # ---- greedy (S2VTModel.py:82-110)
     def _greedy(self, feats):
-        P = {k: v.detach() for k, v in self._params().items()}
         B, L, _ = feats.shape
+        if self._use_xdec():
+            X = self._xdec_state()
+            tokens = torch.empty(B, L - 1, dtype=torch.int64, device=feats.device)
+            X["ws"] = ops.xdec_greedy(X["cfg"], X["wbuf"], feats, tokens, X["ws"])
+            return tokens
+        P = {k: v.detach() for k, v in self._params().items()}
         H, E, V = self.dim_hid, self.dim_embed, self.vocab_size
         T = 2 * L - 1
         dev = feats.device
@@ -527,6 +557,19 @@ class S2VT(nn.Module):
         dev = feats.device
         if V < self.beam_topk:
             raise RuntimeError("beam search expands topk(%d) (S2VTModel.py:216): vocab_size must be >= %d" % (self.beam_topk, self.beam_topk))
+        if self._use_xdec(beam_width):
+            X = self._xdec_state()
+            pen = X["pen"].get(max_beam_depth)
+            if pen is None:         # BeamSearchNode.eval: logp / pow(float(leng), 0.7) -- divisor computed in Python double precision
+                pen = torch.tensor([0.0] + [pow(float(n), 0.7) for n in range(1, max_beam_depth + 3)], dtype=torch.float32).to(dev)
+                X["pen"][max_beam_depth] = pen
+            if X["flag"] is None:
+                X["flag"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+            toks = torch.empty(B, max_beam_depth + 1, dtype=torch.int64, device=dev)
+            lens = torch.empty(B, dtype=torch.int32, device=dev)
+            X["ws"] = ops.xdec_beam(X["cfg"], X["wbuf"], feats, int(beam_width), int(max_beam_depth), self.beam_topk, pen, toks, lens,
+                                    X["ws"], int(self.beam_check_every), X["flag"])
+            return toks, lens
         b1, b2 = _bias_sums(P)
         _, out1, _, _, h1, c1 = _encode_vid_f32(P, feats, L, False, b1)
         pre2 = _word_pre_vid_f32(P, out1, L * B, b2, E, H)

@@ -229,4 +229,73 @@ def beam_search_f32(B: int, H: int, E: int, V: int, beam_width: int, max_depth: 
     L.check(rc, "s2vt_beam_search_f32")
 
 
+# ---------------------------------------------------------------------------------------------------------
+# exact-grade tensor-core path (csrc/xdec_sm100.cu)
+def xgemm_f32(M: int, N: int, K: int, A: torch.Tensor, lda: int, B: torch.Tensor, ldb: int, C: torch.Tensor, cmap: RowMap,
+              bias: Optional[torch.Tensor] = None, accumulate: bool = False) -> None:
+    """C = A . B^T (+ bias) (+ C) with fp32 operands split into fp16 (hi, lo) planes on the fly; tcgen05, fp32-grade accuracy."""
+    _f32(A, "A"); _f32(B, "B"); _f32(C, "C")
+    L.require_cuda(A, B, C, bias)
+    lib = L.load()
+    ws = torch.empty(int(lib.s2vt_xgemm_ws_bytes(M, N, K)), dtype=torch.uint8, device=A.device)
+    with _timed("xgemm_f32", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+        rc = lib.s2vt_xgemm_f32(L.stream_ptr(A.device), M, N, K, L.ptr(A), lda, L.ptr(B), ldb, L.ptr(C), cmap, L.ptr(bias),
+                                int(accumulate), L.ptr(ws))
+    L.check(rc, "s2vt_xgemm_f32")
+
+
+def xdec_cfg(V: int, F: int, Lq: int, H: int, E: int, sos: int, eos: int) -> "L.XdecCfg":
+    return L.XdecCfg(int(V), int(F), int(Lq), int(H), int(E), int(sos), int(eos))
+
+
+def xdec_prepare(cfg, params) -> torch.Tensor:
+    """fp16-plane copies of the 13 weights + the embedding-product table; returns the caller-owned weight buffer."""
+    import ctypes as C
+    lib = L.load()
+    L.require_cuda(*params)
+    for p in params:
+        _f32(p, "parameter")
+    dev = params[0].device
+    wbuf = torch.empty(int(lib.s2vt_xdec_weights_bytes(cfg)), dtype=torch.uint8, device=dev)
+    arr = (C.c_void_p * 13)(*[p.data_ptr() for p in params])
+    with _timed("xdec_prepare"):
+        rc = lib.s2vt_xdec_prepare(L.stream_ptr(dev), cfg, arr, L.ptr(wbuf))
+    L.check(rc, "s2vt_xdec_prepare")
+    return wbuf
+
+
+def xdec_greedy(cfg, wbuf: torch.Tensor, feats: torch.Tensor, tokens: torch.Tensor, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _f32(feats, "feats")
+    L.require_cuda(wbuf, feats, tokens)
+    lib = L.load()
+    B = feats.shape[0]
+    need = int(lib.s2vt_xdec_greedy_ws_bytes(cfg, B))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=feats.device)
+    flops = 2.0 * B * (cfg.length * cfg.feat_dim * cfg.dim_hid + (5 * cfg.length - 3) * 4 * cfg.dim_hid * cfg.dim_hid
+                       + (cfg.length - 1) * cfg.dim_hid * cfg.vocab_size)
+    with _timed("xdec_greedy", flops):
+        rc = lib.s2vt_xdec_greedy(L.stream_ptr(feats.device), cfg, L.ptr(wbuf), B, L.ptr(feats), L.ptr(tokens), L.ptr(ws))
+    L.check(rc, "s2vt_xdec_greedy")
+    return ws
+
+
+def xdec_beam(cfg, wbuf: torch.Tensor, feats: torch.Tensor, beam_width: int, max_depth: int, topk: int, len_pen: torch.Tensor,
+              out_tokens: torch.Tensor, out_len: torch.Tensor, ws: Optional[torch.Tensor] = None, check_every: int = 0,
+              host_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _f32(feats, "feats")
+    L.require_cuda(wbuf, feats, len_pen, out_tokens, out_len)
+    lib = L.load()
+    B = feats.shape[0]
+    need = int(lib.s2vt_xdec_beam_ws_bytes(cfg, B, beam_width, max_depth))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=feats.device)
+    with _timed("xdec_beam"):
+        rc = lib.s2vt_xdec_beam(L.stream_ptr(feats.device), cfg, L.ptr(wbuf), B, L.ptr(feats), beam_width, max_depth, topk,
+                                L.ptr(len_pen), L.ptr(out_tokens), L.ptr(out_len), L.ptr(ws), int(check_every),
+                                host_flag.data_ptr() if host_flag is not None else None)
+    L.check(rc, "s2vt_xdec_beam")
+    return ws
+
+
 __all__ = [n for n in dir() if n.endswith("_f32")] + ["RowMap", "dense", "rowmap"]

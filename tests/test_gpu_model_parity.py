@@ -74,22 +74,24 @@ def test_fused_forward_loss_matches(dev, name):
         assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, k
 
 
+@pytest.mark.parametrize("dec", ["x", "fp32"])          # tcgen05 fp16-split path (default) and the CUDA-core FFMA path
 @pytest.mark.parametrize("name", ["tiny", "mid", "msvd", "msvd_peaky", "paper"])
-def test_greedy_tokens_bit_exact(dev, name):
+def test_greedy_tokens_bit_exact(dev, name, dec):
     g = load_golden(name)
     P, feats, targets, mask, c = golden_inputs(g)
-    model = build_model(c, P, dev).eval()
+    model = build_model(c, P, dev, decode_precision=dec).eval()
     with torch.no_grad():
         pred = model(torch.from_numpy(feats).to(dev), mode="test")
     assert pred.dtype == torch.int64 and tuple(pred.shape) == (c["B"], c["L"] - 1)
     assert np.array_equal(pred.cpu().numpy(), g["greedy"])
 
 
+@pytest.mark.parametrize("dec", ["x", "fp32"])
 @pytest.mark.parametrize("name", ["tiny", "mid", "msvd", "msvd_peaky"])
-def test_beam_tokens_bit_exact(dev, name):
+def test_beam_tokens_bit_exact(dev, name, dec):
     g = load_golden(name)
     P, feats, targets, mask, c = golden_inputs(g)
-    model = build_model(c, P, dev).eval()
+    model = build_model(c, P, dev, decode_precision=dec).eval()
     tf = torch.from_numpy(feats).to(dev)
     for key in [k for k in g if k.startswith("beam")]:
         bw = int(key[4:])

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--beam", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--decode", default="x", choices=["x", "fp32"], help="x: tcgen05 fp16-split path, fp32: CUDA-core FFMA path")
+    ap.add_argument("--beam-batch", type=int, default=256)
     ap.add_argument("--cpu-videos", type=int, default=0, help="also time the CPU port's greedy decode on this many videos")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -38,11 +40,13 @@ def main():
         os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = s2vt_b200.S2VT(CFG["V"], CFG["F"], CFG["L"], dim_hid=CFG["H"], dim_embed=CFG["E"]).to(dev).eval()
+    model = s2vt_b200.S2VT(CFG["V"], CFG["F"], CFG["L"], dim_hid=CFG["H"], dim_embed=CFG["E"], decode_precision=args.decode).to(dev).eval()
     lo, hi = shard_range(args.videos, rank, world)
     n = hi - lo
     g = torch.Generator().manual_seed(77 + rank)
     feats = torch.randn(n, CFG["L"], CFG["F"], generator=g).to(dev)
+
+    enq = []
 
     def timed(fn):
         fn()                                     # warm-up
@@ -53,7 +57,9 @@ def main():
         for _ in range(args.reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            h0 = time.perf_counter()
             fn()
+            enq.append((time.perf_counter() - h0) * 1e3)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -68,14 +74,16 @@ def main():
 
     def beam_all():
         with torch.no_grad():
-            return [model.beam_search_ids(feats[i:i + 256], beam_width=args.beam, max_beam_depth=30) for i in range(0, n, 256)]
+            return [model.beam_search_ids(feats[i:i + 256], beam_width=args.beam, max_beam_depth=30) for i in range(0, n, args.beam_batch)]
 
     ms_g = timed(greedy_all)
+    enq_g = float(np.median(enq)); enq.clear()
     ms_b = timed(beam_all)
-    out = {"n_gpus": world, "videos": args.videos, "greedy_captions_per_s": round(args.videos / (ms_g / 1e3), 1), "greedy_ms": round(ms_g, 2),
+    enq_b = float(np.median(enq))
+    out = {"n_gpus": world, "videos": args.videos, "greedy_captions_per_s": round(args.videos / (ms_g / 1e3), 1), "greedy_ms": round(ms_g, 2), "greedy_host_enqueue_ms": round(enq_g, 2), "beam_host_enqueue_ms": round(enq_b, 2),
            "beam_width": args.beam, "beam_captions_per_s": round(args.videos / (ms_b / 1e3), 1), "beam_ms": round(ms_b, 2),
-           "precision": "fp32 exact (token ids bit-identical to the reference, tests/test_gpu_model_parity.py)",
-           "greedy_batch": args.batch, "beam_batch": 256, "max_beam_depth": 30}
+           "precision": "fp32-grade (token ids bit-identical to the reference, tests/test_gpu_model_parity.py)", "decode_path": args.decode,
+           "greedy_batch": args.batch, "beam_batch": args.beam_batch, "max_beam_depth": 30}
     if args.cpu_videos and rank == 0:
         from oracle.torch_port import S2VTCpuPort
         torch.set_num_threads(os.cpu_count() or 1)
