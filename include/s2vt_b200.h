@@ -338,6 +338,10 @@ int64_t s2vt_xgemm_ws_bytes(int M, int N, int K);
 int s2vt_xgemm_f32(void* stream, int M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
                    float* C, s2vt_rowmap cmap, const float* bias, int accumulate, void* ws);
 
+/* Debug: %globaltimer stamps of CTA (0,0) of every following tensor-core decode kernel into buf[max_records][8] u64 (device
+ * memory; NULL stops).  Returns the number of records handed out since the previous call (tools/trace_xdec.py). */
+int s2vt_xdec_set_trace(void* buf, int max_records);
+
 /* Weight preparation for the decode entry points: fp16 (hi, lo) planes of the 13 state_dict tensors (gate rows interleaved,
  * dimensions padded to multiples of 8) and the table EW = embedding . W_ih(word_rnn)[:, :E]^T  [V, 4H].
  *   params: 13 device pointers in state_dict registration order (S2VTModel.py:19-28)

@@ -31,6 +31,7 @@
 #include "sm100_err.cuh"
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define X_TRY(expr) do { rc = (expr); if (rc) return rc; } while (0)
@@ -57,15 +58,22 @@ struct XParams {
   // LSTM (N = 4*HP, column 4u+g)
   int HP;
   const float* pre; long long pre_ld;
-  const float* gtab; long long gtab_ld; const int* gidx;
-  const float* part_val; const int* part_idx; int n_part;      // previous step's per-tile argmax partials -> token
-  int64_t* tok_out; long long tok_ld; int* tok_i32;            // where n-tile 0 records that token
+  const float* gtab; long long gtab_ld; const int* gidx;       // optional: + gtab[gidx[m]] (the embedding half of word_rnn's input)
   const float* c_in; float* c_out;
   float* h_f32; long long h_ld;
   __half* hp; long long hp_ld; long long hp_plane;             // h planes (scale 2^15)
-  // ARGMAX / BEAM partial outputs, [M, gridDim.x]
+  // BEAM partial outputs (two per tile: one per epilogue warp group)
   float* o_val; int* o_idx; float* o_ms;
+  unsigned long long* o_key;                                   // ARGMAX: per-row packed (value, index) maximum, zeroed by the consumer
+  // LSTM: the previous step's argmax keys -> token (gidx == nullptr); n-tile 0 records it and clears the keys of the next step
+  const unsigned long long* key_in; unsigned long long* key_clear; int64_t* tok_out; long long tok_ld;
+  unsigned long long* trace;   // debug: 8 %globaltimer stamps of CTA (0,0) (tools/trace_xdec.py), or nullptr
 };
+
+// Programmatic dependent launch: a step kernel is launched while its predecessor in the stream still runs; everything that
+// reads the predecessor's output sits behind pdl_wait(), everything before it (barrier / TMEM set-up, weight tiles) overlaps.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
@@ -78,16 +86,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// argmax over the per-tile partials of one row: highest value, lowest index on ties (torch.argmax / max(1))
-__device__ __forceinline__ int reduce_partials(const float* __restrict__ pv, const int* __restrict__ pi, int n) {
-  float bv = pv[0];
-  int bi = pi[0];
-  for (int j = 1; j < n; ++j) {
-    const float v = pv[j];
-    if (v > bv) { bv = v; bi = pi[j]; }
-  }
-  return bi;
+__device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
 }
+__device__ __forceinline__ int key_index(unsigned long long k) { return (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)); }
 
 // r[j] = bits of (main0 + main1 + main2) + corr for 32 columns of this warp's 32 rows (fp32 adds, round to nearest)
 template <int BN>
@@ -127,6 +131,8 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  unsigned long long* const trace = (p.trace && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = ptx::globaltimer_ns();
 
   if (warp_idx == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
@@ -148,11 +154,24 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
+  pdl_launch_dependents();
 
   if (warp_idx == 0) {
     // ===================== TMA producer: both planes of a tile arrive with one 3-D box each =====================
     if (ptx::elect_one()) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      // the B operand is always a weight: its first tiles are requested before the previous kernel's results are awaited
+      const int npre = p.num_kb < STAGES ? p.num_kb : STAGES;
+      for (int kb = 0; kb < npre; ++kb) {
+        const uint32_t fb = ptx::smem_u32(&full_bar[kb]);
+        ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
+        tma_load_3d(smem_base + kb * STAGE_BYTES + 2 * PLANE_A, &tmB, fb, kb * BK, n0, 0);
+      }
+      if (trace) trace[1] = ptx::globaltimer_ns();
+      pdl_wait();
+      if (trace) trace[2] = ptx::globaltimer_ns();
+      for (int kb = 0; kb < npre; ++kb)
+        tma_load_3d(smem_base + kb * STAGE_BYTES, &tmA, ptx::smem_u32(&full_bar[kb]), kb * BK, m0, 0);
+      for (int kb = npre; kb < p.num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         if (!ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1)) { atomicExch(&g_sm100_error, 11); break; }
@@ -163,6 +182,7 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tma_load_3d(sB, &tmB, fb, kb * BK, n0, 0);
       }
     }
+    __syncwarp();
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
@@ -172,6 +192,8 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t ph = (kb / STAGES) & 1;
         if (!ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph)) { atomicExch(&g_sm100_error, 12); break; }
         ptx::tc_fence_after();
+        if (trace && kb == 0) trace[3] = ptx::globaltimer_ns();
+        if (trace && kb == p.num_kb - 1) trace[4] = ptx::globaltimer_ns();
         const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + 2 * PLANE_A;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
@@ -188,38 +210,65 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       ptx::mma_commit(ptx::smem_u32(&tmem_full_bar));
     }
-  } else if (warp_idx >= 4) {
-    // ===================== epilogue =====================
-    const int e = warp_idx - 4;
-    const int m = m0 + e * 32 + lane;
+    __syncwarp();
+  }
+
+  // ===================== epilogue: all eight warps =====================
+  // A warp may read the TMEM lanes of its quarter (warp_idx % 4) only: warps q and q+4 share 32 rows and split the tile's
+  // 32-column chunks between them (`half` 0 takes the even chunks, 1 the odd ones).
+  {
+    const int q = warp_idx & 3, half = warp_idx >> 2;
+    const int m = m0 + q * 32 + lane;
     const bool row_ok = m < p.M;
     const float sc = (p.a_inv ? __ldg(p.a_inv) : 1.f) * (p.b_inv ? __ldg(p.b_inv) : 1.f);
-    const uint32_t trow = tmem + ((uint32_t)(e * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const int nmain = p.num_kb < 3 ? p.num_kb : 3;
+    pdl_wait();
 
-    int tok = -1;
+    // ---- LSTM: everything the gates need besides the accumulators is fetched while the MMAs run
+    float pin[32], cp[8];
+    int tok = 0;
+    auto lstm_inputs = [&](int n) {
+      const float4* src = reinterpret_cast<const float4*>(p.pre ? p.pre + (long long)m * p.pre_ld + n : p.bias + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 t = __ldg(src + j); pin[4 * j] = t.x; pin[4 * j + 1] = t.y; pin[4 * j + 2] = t.z; pin[4 * j + 3] = t.w; }
+      if (p.gtab) {
+        const float4* g = reinterpret_cast<const float4*>(p.gtab + (long long)tok * p.gtab_ld + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float4 t = __ldg(g + j); pin[4 * j] += t.x; pin[4 * j + 1] += t.y; pin[4 * j + 2] += t.z; pin[4 * j + 3] += t.w; }
+      }
+      if (p.c_in) {
+        const float4* c4 = reinterpret_cast<const float4*>(p.c_in + (long long)m * p.HP + (n >> 2));
+        const float4 t0 = c4[0], t1 = c4[1];
+        cp[0] = t0.x; cp[1] = t0.y; cp[2] = t0.z; cp[3] = t0.w; cp[4] = t1.x; cp[5] = t1.y; cp[6] = t1.z; cp[7] = t1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+      }
+    };
     if (EPI == EPI_LSTM) {
       if (p.gtab && row_ok) {
-        if (p.part_val) {
-          tok = reduce_partials(p.part_val + (long long)m * p.n_part, p.part_idx + (long long)m * p.n_part, p.n_part);
-          if (blockIdx.x == 0) {
+        if (p.gidx) tok = p.gidx[m];
+        else {
+          tok = key_index(__ldcg(p.key_in + m));
+          if (blockIdx.x == 0 && half == 0) {
             if (p.tok_out) p.tok_out[(long long)m * p.tok_ld] = tok;
-            if (p.tok_i32) p.tok_i32[m] = tok;
+            if (p.key_clear) p.key_clear[m] = 0ull;
           }
-        } else {
-          tok = p.gidx[m];
         }
       }
+      if (row_ok && n0 + half * 32 < p.N) lstm_inputs(n0 + half * 32);
     }
 
     bool ok = ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar), 0);
     if (!ok) atomicExch(&g_sm100_error, 13);
     ptx::tc_fence_after();
+    if (trace && threadIdx.x == 128) trace[5] = ptx::globaltimer_ns();
 
     if (EPI == EPI_STORE) {
       const long long crow = row_ok ? p.cm(m) : 0;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;
         uint32_t r[32];
@@ -250,43 +299,20 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (EPI == EPI_LSTM) {
       // columns n..n+31 = units u0..u0+7, gates (i,f,g,o) adjacent; N = 4*HP is a multiple of 32
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;
         uint32_t r[32];
         load_acc<BN>(trow + (uint32_t)(c * 32), nmain, r);
         if (!row_ok) continue;
+        if (c != half) lstm_inputs(n);
         const int u0 = n >> 2;
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * sc;
-        if (p.pre) {
-          const float4* src = reinterpret_cast<const float4*>(p.pre + (long long)m * p.pre_ld + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = __ldg(src + j); x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w; }
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = __ldg(src + j); x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w; }
-        }
-        if (tok >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(p.gtab + (long long)tok * p.gtab_ld + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = __ldg(src + j); x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w; }
-        }
-        float cp[8];
-        if (p.c_in) {
-          const float4* src = reinterpret_cast<const float4*>(p.c_in + (long long)m * p.HP + u0);
-          const float4 t0 = src[0], t1 = src[1];
-          cp[0] = t0.x; cp[1] = t0.y; cp[2] = t0.z; cp[3] = t0.w; cp[4] = t1.x; cp[5] = t1.y; cp[6] = t1.z; cp[7] = t1.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cp[j] = 0.f;
-        }
         float cn[8], h[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float ig = sigmoidf_exact(x[4 * j]), fg = sigmoidf_exact(x[4 * j + 1]), gg = tanhf(x[4 * j + 2]), og = sigmoidf_exact(x[4 * j + 3]);
+          const float xi = __uint_as_float(r[4 * j]) * sc + pin[4 * j], xf = __uint_as_float(r[4 * j + 1]) * sc + pin[4 * j + 1];
+          const float xg = __uint_as_float(r[4 * j + 2]) * sc + pin[4 * j + 2], xo = __uint_as_float(r[4 * j + 3]) * sc + pin[4 * j + 3];
+          const float ig = sigmoidf_exact(xi), fg = sigmoidf_exact(xf), gg = tanhf(xg), og = sigmoidf_exact(xo);
           cn[j] = fg * cp[j] + ig * gg;
           h[j] = og * tanhf(cn[j]);
         }
@@ -318,7 +344,7 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float bv = -INFINITY;
       int bi = 0x7fffffff;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;
         uint32_t r[32];
@@ -331,18 +357,17 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
-      if (row_ok) {
-        p.o_val[(long long)m * gridDim.x + blockIdx.x] = bv;
-        p.o_idx[(long long)m * gridDim.x + blockIdx.x] = bi;
-      }
+      // one 64-bit atomicMax per row and warp: key = (order-preserving bits of the value) : (~index), so the maximum is the
+      // highest value and, among equal values, the lowest index (torch.argmax)
+      if (row_ok && bi != 0x7fffffff) atomicMax(p.o_key + m, pack_key(bv, bi));
     } else {   // EPI_BEAM
       float mx = -INFINITY, sum = 0.f;
       float tv[KC];
       int ti[KC];
 #pragma unroll
-      for (int q = 0; q < KC; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+      for (int qq = 0; qq < KC; ++qq) { tv[qq] = -INFINITY; ti[qq] = 0x7fffffff; }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;
         uint32_t r[32];
@@ -364,23 +389,24 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (v[j] > tv[KC - 1]) {                      // strict: an equal value keeps the earlier (lower) index ahead
             tv[KC - 1] = v[j]; ti[KC - 1] = n + j;
 #pragma unroll
-            for (int q = KC - 1; q > 0; --q) {
-              if (tv[q] > tv[q - 1]) {
-                const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
-                const int iv = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = iv;
+            for (int qq = KC - 1; qq > 0; --qq) {
+              if (tv[qq] > tv[qq - 1]) {
+                const float fv = tv[qq]; tv[qq] = tv[qq - 1]; tv[qq - 1] = fv;
+                const int iv = ti[qq]; ti[qq] = ti[qq - 1]; ti[qq - 1] = iv;
               }
             }
           }
         }
       }
-      if (row_ok) {
-        const long long o = (long long)m * gridDim.x + blockIdx.x;
+      if (row_ok) {                                     // partials are [M][part], part = 2*tile + half (a half may be empty: -inf / 0)
+        const long long o = (long long)m * (2 * gridDim.x) + 2 * blockIdx.x + half;
         p.o_ms[2 * o] = mx; p.o_ms[2 * o + 1] = sum;
 #pragma unroll
-        for (int q = 0; q < KC; ++q) { p.o_val[o * KC + q] = tv[q]; p.o_idx[o * KC + q] = ti[q]; }
+        for (int qq = 0; qq < KC; ++qq) { p.o_val[o * KC + qq] = tv[qq]; p.o_idx[o * KC + qq] = ti[qq]; }
       }
     }
   }
+  if (trace && threadIdx.x == 128) trace[6] = ptx::globaltimer_ns();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp_idx == 2) ptx::tmem_dealloc(tmem, 4 * BN);
@@ -445,12 +471,10 @@ __global__ void fill_i32_kernel(int* __restrict__ p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
-// final greedy pick (the LSTM epilogue resolves every earlier step's token itself)
-__global__ void greedy_pick_kernel(int M, const float* __restrict__ pv, const int* __restrict__ pi, int n_part,
-                                   int64_t* __restrict__ tok_out, long long tok_ld) {
+// the last greedy step's token (every earlier one is resolved by the following step's LSTM epilogue)
+__global__ void keys_to_tokens_kernel(int M, const unsigned long long* __restrict__ key, int64_t* __restrict__ tok_out, long long tok_ld) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  tok_out[(long long)m * tok_ld] = reduce_partials(pv + (long long)m * n_part, pi + (long long)m * n_part, n_part);
+  if (m < M) tok_out[(long long)m * tok_ld] = key_index(key[m]);
 }
 
 // ------------------------------------------------------------------ beam bookkeeping
@@ -521,11 +545,12 @@ __global__ void beam_init_kernel(int B, int bw, int D1, int sos, BeamMeta m, int
 // at most beam_width entries leave the queue per depth.
 __global__ void beam_select_kernel(int B, int bw, int topk, int kc, int D1, int eos, const float* __restrict__ len_pen,
                                    BeamMeta old_, BeamMeta new_, const float* __restrict__ cand_lp, const int* __restrict__ cand_tok,
-                                   int* __restrict__ nbeam, int* __restrict__ done, int* __restrict__ parent,
-                                   int64_t* __restrict__ out_tokens, int* __restrict__ out_len, int* __restrict__ n_done) {
+                                   int* __restrict__ nbeam, int* __restrict__ done, int* __restrict__ was_done, int* __restrict__ parent,
+                                   int* __restrict__ out_len, int* __restrict__ n_done) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= B) return;
   const int base = v * bw;
+  was_done[v] = done[v];
   if (done[v]) {
     for (int j = 0; j < bw; ++j) {
       const int s = base + j;
@@ -559,23 +584,16 @@ __global__ void beam_select_kernel(int B, int bw, int topk, int kc, int D1, int 
     }
     const int s = base + bj;
     const int ln = old_.len[s];
-    int* hn = new_.hist + (long long)d * D1;
-    const int* ho = old_.hist + (long long)s * D1;
-    for (int q = 0; q < D1; ++q) hn[q] = ho[q];
+    // token histories are not copied here: slot d inherits its parent's row in beam_hist_kernel (one warp per slot)
     if (old_.fin[s]) {
       new_.key[d] = old_.key[s]; new_.tok[d] = old_.tok[s]; new_.len[d] = ln; new_.fin[d] = 1;
     } else {
       const int tk = cand_tok[(long long)s * kc + ptr[bj]];
       new_.key[d] = bestk; new_.tok[d] = tk; new_.len[d] = ln + 1; new_.fin[d] = (tk == eos) ? 1 : 0;
-      if (ln < D1) hn[ln] = tk;
     }
     ptr[bj] += 1;
     parent[d] = s;
-    if (r == 0) {
-      const int Ln = new_.len[d];
-      for (int q = 0; q < D1; ++q) out_tokens[(long long)v * D1 + q] = q < Ln ? hn[q] : -1;
-      out_len[v] = Ln;
-    }
+    if (r == 0) out_len[v] = new_.len[d];
   }
   for (int r = take; r < bw; ++r) {
     const int d = base + r;
@@ -584,6 +602,24 @@ __global__ void beam_select_kernel(int B, int bw, int topk, int kc, int D1, int 
   }
   nbeam[v] = take;
   if (last) { done[v] = 1; atomicAdd(n_done, 1); }
+}
+
+// Token histories after a selection: slot d's row = its parent's row (+ the token just appended); slot 0 of a video (the head
+// of its queue) is also the video's answer so far.  grid = S slots, one warp each.  `was_done` = done[] before this selection.
+__global__ void beam_hist_kernel(int bw, int D1, BeamMeta old_, BeamMeta new_, const int* __restrict__ parent, const int* __restrict__ was_done,
+                                 int64_t* __restrict__ out_tokens) {
+  const int d = blockIdx.x, v = d / bw;
+  if (was_done[v]) return;                                    // frozen video: its answer is final, its rows are never read again
+  const bool unused = (new_.key[d] == INFINITY);
+  const int s = parent[d];
+  const bool fresh = !unused && !old_.fin[s];                 // a live hypothesis extended by new_.tok[d]
+  const int Ln = new_.len[d];
+  for (int q = threadIdx.x; q < D1; q += 32) {
+    int t = unused ? -1 : old_.hist[(long long)s * D1 + q];
+    if (fresh && q == Ln - 1) t = new_.tok[d];
+    new_.hist[(long long)d * D1 + q] = t;
+    if (d == v * bw) out_tokens[(long long)v * D1 + q] = (q < Ln) ? t : -1;
+  }
 }
 
 // Per-slot state after a depth, re-ordered by parent.  Plane buffers hold fp16 (hi, lo) rows of HP elements.
@@ -638,6 +674,9 @@ struct Planes {            // an fp16 (hi, lo) operand: rows x k, leading dimens
   const __half* p; long long ld; long long plane; const float* inv;
 };
 
+static unsigned long long* g_trace_buf = nullptr;     // s2vt_xdec_set_trace: [max][8] stamps, one record per xgemm launch
+static int g_trace_max = 0, g_trace_n = 0;
+
 template <int BN, int EPI>
 static int launch_x(cudaStream_t st, int M, int N, int K, const Planes& A, const Planes& B, XParams p) {
   constexpr int STAGES = (BN == 128) ? 3 : 4;
@@ -649,13 +688,23 @@ static int launch_x(cudaStream_t st, int M, int N, int K, const Planes& A, const
   if (rc) return rc;
   p.M = M; p.N = N; p.K = K; p.num_kb = (K + BK - 1) / BK;
   p.a_inv = A.inv; p.b_inv = B.inv;
+  if (g_trace_buf && g_trace_n < g_trace_max) {
+    p.trace = g_trace_buf + 8 * (size_t)g_trace_n++;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     S2VT_CHECK_CUDA(cudaFuncSetAttribute(xgemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  xgemm_kernel<BN, EPI><<<grid, 256, SMEM, st>>>(tmA, tmB, p);
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("S2VT_XDEC_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ceil_div(N, BN), ceil_div(M, BM)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xgemm_kernel<BN, EPI>, tmA, tmB, p));
   S2VT_CHECK_LAUNCH();
   return 0;
 }
@@ -740,17 +789,17 @@ static int side_stream(cudaStream_t* out) {
 struct StepArgs {
   const float* pre; long long pre_ld; const float* bias;
   const float* gtab; long long gtab_ld; const int* gidx;
-  const float* part_val; const int* part_idx; int n_part; int64_t* tok_out; long long tok_ld; int* tok_i32;
+  const unsigned long long* key_in; unsigned long long* key_clear; int64_t* tok_out; long long tok_ld;
   const float* c_in; float* c_out; __half* hp; long long hp_ld; long long hp_plane; float* h_f32; long long h_ld;
 };
 static int x_lstm_step(cudaStream_t st, int M, int HP, int K, const Planes& A, const Planes& W, const StepArgs& a) {
   XParams p{};
   p.HP = HP; p.pre = a.pre; p.pre_ld = a.pre_ld; p.bias = a.bias;
   p.gtab = a.gtab; p.gtab_ld = a.gtab_ld; p.gidx = a.gidx;
-  p.part_val = a.part_val; p.part_idx = a.part_idx; p.n_part = a.n_part; p.tok_out = a.tok_out; p.tok_ld = a.tok_ld; p.tok_i32 = a.tok_i32;
+  p.key_in = a.key_in; p.key_clear = a.key_clear; p.tok_out = a.tok_out; p.tok_ld = a.tok_ld;
   p.c_in = a.c_in; p.c_out = a.c_out; p.hp = a.hp; p.hp_ld = a.hp_ld; p.hp_plane = a.hp_plane; p.h_f32 = a.h_f32; p.h_ld = a.h_ld;
-  // few rows: narrow tiles put the step on twice as many SMs
-  if (M <= 384) return launch_x<64, EPI_LSTM>(st, M, 4 * HP, K, A, W, p);
+  // up to four row tiles: narrow tiles put the step on twice as many SMs (one wave, one 32-column chunk per epilogue warp)
+  if (M <= 512) return launch_x<64, EPI_LSTM>(st, M, 4 * HP, K, A, W, p);
   return launch_x<128, EPI_LSTM>(st, M, 4 * HP, K, A, W, p);
 }
 
@@ -760,8 +809,25 @@ static int x_lstm_step(cudaStream_t st, int M, int HP, int K, const Planes& A, c
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// Encoded maps are a pure function of the arguments; a decode call encodes ~1100 of them and repeats the same ones on every
+// call with the same workspace, so they are memoised per host thread (cuTensorMapEncodeTiled costs ~1.5 us).
+struct TmapKey { const void* base; uint64_t k, rows, ld, plane; uint32_t box; };
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+static thread_local TmapSlot* g_tmap_cache = nullptr;
+constexpr uint32_t TMAP_SLOTS = 8192;
+
 int make_tmap_planes(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint64_t plane_stride,
                      uint32_t box_rows) {
+  if (!g_tmap_cache) g_tmap_cache = new TmapSlot[TMAP_SLOTS]();
+  uint64_t h = reinterpret_cast<uintptr_t>(base) * 0x9E3779B97F4A7C15ull ^ (k * 0xC2B2AE3D27D4EB4Full) ^ (rows * 0x165667B19E3779F9ull) ^
+               (ld << 17) ^ (plane_stride << 3) ^ box_rows;
+  h ^= h >> 29;
+  TmapSlot& slot = g_tmap_cache[(uint32_t)(h % TMAP_SLOTS)];
+  if (slot.used && slot.key.base == base && slot.key.k == k && slot.key.rows == rows && slot.key.ld == ld && slot.key.plane == plane_stride &&
+      slot.key.box == box_rows) {
+    *out = slot.map;
+    return 0;
+  }
   static EncodeTiledFn3 enc = nullptr;
   if (!enc) {
     void* fp = nullptr;
@@ -781,6 +847,9 @@ int make_tmap_planes(CUtensorMap* out, const void* base, uint64_t k, uint64_t ro
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (planes) failed with CUresult %d (k=%llu rows=%llu ld=%llu plane=%llu)", (int)r,
                                      (unsigned long long)k, (unsigned long long)rows, (unsigned long long)ld, (unsigned long long)plane_stride);
+  slot.key = TmapKey{base, k, rows, ld, plane_stride, box_rows};
+  slot.map = *out;
+  slot.used = true;
   return 0;
 }
 
@@ -792,6 +861,15 @@ using namespace s2vt;
 using namespace s2vt::xd;
 
 // ====================================================================== C ABI
+/* Debug: stamp %globaltimer at the phases of CTA (0,0) of every following xgemm launch into buf[max_records][8]
+ * (0 start, 1 weights requested, 2 predecessor done, 3 first tile landed, 4 last tile landed, 5 accumulators complete,
+ * 6 epilogue done); buf = NULL stops.  Returns the number of records handed out so far. */
+extern "C" int s2vt_xdec_set_trace(void* buf, int max_records) {
+  const int n = g_trace_n;
+  g_trace_buf = (unsigned long long*)buf; g_trace_max = buf ? max_records : 0; g_trace_n = 0;
+  return n;
+}
+
 extern "C" int64_t s2vt_xgemm_ws_bytes(int M, int N, int K) {
   const long long KP = rup(K, 8);
   return (int64_t)(2 * 2 * ((long long)M + N) * KP + 1024 + 256);
@@ -877,8 +955,9 @@ namespace {
 struct GreedyWs {
   float* inv; unsigned int* bits;
   __half *fa, *xp, *o1p, *h2p;
-  float *xproj, *pre1, *pre2, *c1, *c2, *pv;
-  int *pi, *sos;
+  float *xproj, *pre1, *pre2, *c1, *c2;
+  int* sos;
+  unsigned long long* key;       // [3][B] argmax keys, rotating over the decode steps (written k, read k+1, cleared k+2)
   size_t bytes;
 };
 GreedyWs carve_greedy(char* base, const Cfg& g, int B, int T1 /* vid_rnn steps */) {
@@ -897,9 +976,8 @@ GreedyWs carve_greedy(char* base, const Cfg& g, int B, int T1 /* vid_rnn steps *
   w.h2p = (__half*)take(2 * 2 * 2 * (size_t)B * g.HP);
   w.c1 = (float*)take(4 * 2 * (size_t)B * g.HP);
   w.c2 = (float*)take(4 * 2 * (size_t)B * g.HP);
-  w.pv = (float*)take(4 * (size_t)B * n_part);
-  w.pi = (int*)take(4 * (size_t)B * n_part);
   w.sos = (int*)take(4 * (size_t)B);
+  w.key = (unsigned long long*)take(8 * 3 * (size_t)B);
   w.bytes = off;
   return w;
 }
@@ -977,6 +1055,7 @@ extern "C" int s2vt_xdec_greedy(void* stream, s2vt_xdec_cfg cfg, const void* wbu
   const int n_part = ceil_div(g.V, 128);
   fill_i32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.sos, B, g.sos);
   S2VT_CHECK_LAUNCH();
+  S2VT_CHECK_CUDA(cudaMemsetAsync(w.key, 0, 8 * 3 * (size_t)B, st));
   X_TRY(encode(st, sd, g, W, w, B, feats, T));
   // decode steps on the side stream (it already holds word_rnn's encode steps): word_rnn step -> out_linear + argmax
   const Planes WH2{W.hh2, HP, (long long)G * HP, W.inv + INV_HH2}, WO{W.out, HP, (long long)g.V * HP, W.inv + INV_OUT};
@@ -986,17 +1065,18 @@ extern "C" int s2vt_xdec_greedy(void* stream, s2vt_xdec_cfg cfg, const void* wbu
     a.pre = w.pre2 + (long long)t * B * G; a.pre_ld = G; a.bias = W.b2;
     a.gtab = W.ew; a.gtab_ld = G;
     if (k == 0) a.gidx = w.sos;
-    else { a.part_val = w.pv; a.part_idx = w.pi; a.n_part = n_part; a.tok_out = tokens + (k - 1); a.tok_ld = L - 1; }
+    else { a.key_in = w.key + (size_t)((k - 1) % 3) * B; a.tok_out = tokens + (k - 1); a.tok_ld = L - 1; }
+    a.key_clear = w.key + (size_t)((k + 1) % 3) * B;          // the keys step k+1 will accumulate into (last read by step k-1)
     a.c_in = w.c2 + (long long)((t - 1) & 1) * BH; a.c_out = w.c2 + (long long)(t & 1) * BH;
     a.hp = w.h2p + (long long)((t + 1) & 1) * BH; a.hp_ld = HP; a.hp_plane = 2 * BH;
     Planes A2{w.h2p + (long long)(t & 1) * BH, HP, 2 * BH, W.inv + INV_H};
     X_TRY(x_lstm_step(sd, B, HP, HP, A2, WH2, a));
     XParams p{};
-    p.bias = W.bout; p.o_val = w.pv; p.o_idx = w.pi;
+    p.bias = W.bout; p.o_key = w.key + (size_t)(k % 3) * B;
     Planes AH{w.h2p + (long long)((t + 1) & 1) * BH, HP, 2 * BH, W.inv + INV_H};
     X_TRY((launch_x<128, EPI_ARGMAX>(sd, B, g.V, HP, AH, WO, p)));
   }
-  greedy_pick_kernel<<<ceil_div(B, 128), 128, 0, sd>>>(B, w.pv, w.pi, n_part, tokens + (L - 2), L - 1);
+  keys_to_tokens_kernel<<<ceil_div(B, 128), 128, 0, sd>>>(B, w.key + (size_t)((L - 2) % 3) * B, tokens + (L - 2), L - 1);
   S2VT_CHECK_LAUNCH();
   S2VT_CHECK_CUDA(cudaEventRecord(g_ev[2], sd));
   S2VT_CHECK_CUDA(cudaStreamWaitEvent(st, g_ev[2], 0));
@@ -1007,7 +1087,7 @@ namespace {
 struct BeamWs {
   __half *a1, *x, *h2n;
   float *c1, *c1n, *c2, *c2n, *ms, *tv, *cand_lp;
-  int *ti, *cand_tok, *nbeam, *done, *parent, *n_done;
+  int *ti, *cand_tok, *nbeam, *done, *was_done, *parent, *n_done;
   xd::BeamMeta meta[2];
   size_t bytes;
 };
@@ -1022,12 +1102,12 @@ BeamWs carve_beam(char* base, const Cfg& g, int B, int bw, int D1) {
   w.h2n = (__half*)take(2 * 2 * S * HP);
   w.c1 = (float*)take(4 * S * HP); w.c1n = (float*)take(4 * S * HP);
   w.c2 = (float*)take(4 * S * HP); w.c2n = (float*)take(4 * S * HP);
-  w.ms = (float*)take(4 * 2 * S * n_part);
-  w.tv = (float*)take(4 * S * n_part * KC);
-  w.ti = (int*)take(4 * S * n_part * KC);
+  w.ms = (float*)take(4 * 2 * S * 2 * n_part);
+  w.tv = (float*)take(4 * S * 2 * n_part * KC);
+  w.ti = (int*)take(4 * S * 2 * n_part * KC);
   w.cand_lp = (float*)take(4 * S * KC);
   w.cand_tok = (int*)take(4 * S * KC);
-  w.nbeam = (int*)take(4 * (size_t)B); w.done = (int*)take(4 * (size_t)B); w.parent = (int*)take(4 * S);
+  w.nbeam = (int*)take(4 * (size_t)B); w.done = (int*)take(4 * (size_t)B); w.was_done = (int*)take(4 * (size_t)B); w.parent = (int*)take(4 * S);
   w.n_done = (int*)take(64);
   for (int i = 0; i < 2; ++i) {
     w.meta[i].key = (float*)take(4 * S); w.meta[i].tok = (int*)take(4 * S); w.meta[i].len = (int*)take(4 * S);
@@ -1103,10 +1183,12 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
       Planes A{w.h2n, HP, SH, W.inv + INV_H};
       X_TRY((launch_x<128, EPI_BEAM>(st, S, g.V, HP, A, WO, p)));
     }
-    beam_combine_kernel<<<S, 32, (size_t)n_part * KC * 8, st>>>(S, n_part, kc, w.ms, w.tv, w.ti, w.cand_lp, w.cand_tok);
+    beam_combine_kernel<<<S, 32, (size_t)2 * n_part * KC * 8, st>>>(S, 2 * n_part, kc, w.ms, w.tv, w.ti, w.cand_lp, w.cand_tok);
     S2VT_CHECK_LAUNCH();
-    beam_select_kernel<<<ceil_div(B, 64), 64, 0, st>>>(B, beam_width, topk, kc, D1, g.eos, len_pen, mo, mn, w.cand_lp, w.cand_tok,
-                                                      w.nbeam, w.done, w.parent, out_tokens, out_len, w.n_done);
+    beam_select_kernel<<<ceil_div(B, 32), 32, 0, st>>>(B, beam_width, topk, kc, D1, g.eos, len_pen, mo, mn, w.cand_lp, w.cand_tok,
+                                                      w.nbeam, w.done, w.was_done, w.parent, out_len, w.n_done);
+    S2VT_CHECK_LAUNCH();
+    beam_hist_kernel<<<S, 32, 0, st>>>(beam_width, D1, mo, mn, w.parent, w.was_done, out_tokens);
     S2VT_CHECK_LAUNCH();
     beam_gather_kernel<<<dim3(S, 4), 128, 0, st>>>(S, HP, w.parent, w.a1, SH, w.x, 2 * SH, w.h2n, SH, w.c1, w.c1n, w.c2, w.c2n);
     S2VT_CHECK_LAUNCH();

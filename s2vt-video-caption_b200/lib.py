@@ -90,6 +90,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp]),
     "s2vt_xgemm_ws_bytes": (_i64, [_i, _i, _i]),
     "s2vt_xgemm_f32": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, RowMap, _vp, _i, _vp]),
+    "s2vt_xdec_set_trace": (_i, [_vp, _i]),
     "s2vt_xdec_weights_bytes": (_i64, [XdecCfg]),
     "s2vt_xdec_prepare": (_i, [_vp, XdecCfg, _vp, _vp]),
     "s2vt_xdec_greedy_ws_bytes": (_i64, [XdecCfg, _i]),

@@ -117,7 +117,7 @@ def test_beam_msvd_matches_ffma_path(dev, peaky):
         assert torch.equal(t0, t1) and torch.equal(l0, l1)
 
 
-@pytest.mark.parametrize("dims", [(77, 36, 20, 28, 5, 7), (131, 40, 24, 8, 4, 130), (300, 64, 72, 40, 6, 33)])
+@pytest.mark.parametrize("dims", [(77, 36, 20, 28, 5, 7), (131, 40, 24, 8, 4, 130), (300, 64, 72, 40, 6, 33), (120, 40, 32, 24, 5, 400)])
 def test_ragged_shapes_vs_oracle(dev, dims):
     V, F, H, E, Lq, B = dims
     P = O.synth_params(V, F, H, E, seed=V + H, out_scale=20.0, eos_bias=1.5)

@@ -27,7 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--videos", type=int, default=1970)
     ap.add_argument("--beam", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--decode", default="x", choices=["x", "fp32"], help="x: tcgen05 fp16-split path, fp32: CUDA-core FFMA path")
     ap.add_argument("--beam-batch", type=int, default=256)
