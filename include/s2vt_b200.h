@@ -46,6 +46,8 @@ int         s2vt_has_tcgen05(void);
 /* Debug aid: synchronises `stream` and returns the device-side error flag of the tensor-core kernels
  * (0 = none; non-zero = an mbarrier wait timed out, which is never expected). */
 int         s2vt_device_error_flag(void* stream);
+/* Resets that flag (after the caller has reported it). */
+int         s2vt_device_error_clear(void);
 
 /* ------------------------------------------------------------------ exact fp32 GEMM (CUDA cores)
  * C[cmap(m), n] = sum_k A(m,k) * B(n,k) (+ bias[n]) (+ C if accumulate)
@@ -307,6 +309,12 @@ int s2vt_colsum_bf16(void* stream, const void* X_bf16, int64_t M, int N, int64_t
  * a backward call passes it back with have_lse = 1 and reads every logit exactly once.  row_loss / loss may be NULL. */
 int s2vt_ce_bf16(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
                  float* row_loss, float* loss, float* row_lse, int have_lse, void* dlogits_bf16, const float* gscale);
+
+/* s2vt_ce_bf16 with the gradient row of logits row r written at element offset omap(r) of dlogits_bf16: reads the batch-major
+ * fp32 logits the module API returns and writes dL/dlogits time-major, as the backward GEMMs consume it (no transpose pass). */
+int s2vt_ce_bf16_mapped(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
+                        float* row_loss, float* loss, float* row_lse, int have_lse, void* dlogits_bf16, s2vt_rowmap omap,
+                        const float* gscale);
 
 /* ------------------------------------------------------------------ vocab projection fused with the loss statistics
  * logits = A W^T + bias on the tensor cores (A [R,K] bf16, W [V,K] bf16), written ONCE as bf16 [R, ldl]; the GEMM epilogue also

@@ -1,11 +1,13 @@
 """MaskCriterion drop-in (utils.py:6-26) on the sm_100a cross-entropy kernel."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch import nn
 
 from . import ops
-from .lib import dense
+from .lib import dense, rowmap
 
 
 class _MeanCEFn(torch.autograd.Function):
@@ -13,7 +15,18 @@ class _MeanCEFn(torch.autograd.Function):
     def forward(ctx, logits2d, target1d):
         R, V = logits2d.shape
         loss = torch.empty((), device=logits2d.device)
-        ops.ce_f32(logits2d, R, V, target1d, 0, dense(1), loss)
+        # logits produced by this package's tensor-core forward(mode='train'): single-pass CE that keeps each row's log-sum-exp, and a
+        # backward that writes dL/dlogits once, as time-major bf16, straight into the producer (model._TrainLogitsBf16Fn)
+        from . import model as M
+        from . import engine_bf16 as EB
+        prod = M.lookup_logits_producer(logits2d) if ctx.needs_input_grad[0] else None
+        ctx.prod = None
+        if prod is not None:
+            lse = torch.empty(R, dtype=torch.float32, device=logits2d.device)
+            EB.ce_bf16(logits2d, R, V, target1d, 0, dense(1), loss=loss, row_lse=lse)
+            ctx.prod, ctx.lse = weakref.ref(prod), lse
+        else:
+            ops.ce_f32(logits2d, R, V, target1d, 0, dense(1), loss)
         ctx.save_for_backward(logits2d, target1d)
         return loss
 
@@ -21,6 +34,16 @@ class _MeanCEFn(torch.autograd.Function):
     def backward(ctx, g):
         logits2d, target1d = ctx.saved_tensors
         R, V = logits2d.shape
+        prod = ctx.prod() if ctx.prod is not None else None
+        if prod is not None:
+            from . import engine_bf16 as EB
+            B, Lm1 = prod.targets.shape
+            dl = torch.empty(R, V, dtype=torch.bfloat16, device=logits2d.device)
+            # logits row r = b*(L-1) + t  ->  gradient row t*B + b
+            EB.ce_bf16(logits2d, R, V, target1d, 0, dense(1), dlogits=dl, gscale=g.contiguous().to(torch.float32), row_lse=ctx.lse,
+                       have_lse=True, omap=rowmap(Lm1, V, B * V))
+            prod.dl_bf16 = dl if prod.dl_bf16 is None else prod.dl_bf16 + dl
+            return torch.zeros((), device=logits2d.device).expand(R, V), None      # zero-stride placeholder (see the producer's backward)
         dl = torch.empty_like(logits2d)
         scratch = torch.empty((), device=logits2d.device)
         ops.ce_f32(logits2d, R, V, target1d, 0, dense(1), scratch, dlogits=dl, gscale=g.contiguous().to(torch.float32))

@@ -21,6 +21,7 @@ namespace s2vt {
 int make_tmap_any(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, int esize);
 
 int gemm_persist_error_flag() { return read_sm100_error_flag(); }
+int gemm_persist_error_clear() { return clear_sm100_error_flag(); }
 
 constexpr int PBM = 128, PBN = 256, PBK = 64, PSTAGES = 4, PRING = 4, PNSTG = 2;
 constexpr int PA_BYTES = PBM * PBK * 2, PB_BYTES = PBN * PBK * 2, PSTAGE_BYTES = PA_BYTES + PB_BYTES;

@@ -23,6 +23,7 @@
 namespace s2vt {
 
 int lstm_bf16_error_flag() { return read_sm100_error_flag(); }
+int lstm_bf16_error_clear() { return clear_sm100_error_flag(); }
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer);
 
 namespace ptx {

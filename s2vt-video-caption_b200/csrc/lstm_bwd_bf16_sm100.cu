@@ -20,6 +20,7 @@
 namespace s2vt {
 
 int lstm_bwd_bf16_error_flag() { return read_sm100_error_flag(); }
+int lstm_bwd_bf16_error_clear() { return clear_sm100_error_flag(); }
 
 constexpr int BWD_NB = 16;
 

@@ -94,7 +94,7 @@ __device__ __forceinline__ float blk_reduce_sum(float v, float* sh) {
 // row_loss = lse - z[target].  Pass 2 (optional): bf16 dlogits = (softmax - onehot) * gscale / R.
 __global__ void ce_row_bf16_kernel(const float* __restrict__ logits, int V, const int64_t* __restrict__ targets, RowMap tmap,
                                    float* __restrict__ row_loss, float* __restrict__ row_lse, int have_lse,
-                                   __nv_bfloat16* __restrict__ dlogits, const float* __restrict__ gscale, float inv_rows) {
+                                   __nv_bfloat16* __restrict__ dlogits, const float* __restrict__ gscale, float inv_rows, RowMap omap) {
   __shared__ float sh[32];
   const long long r = blockIdx.x;
   const float* z = logits + r * V;
@@ -128,7 +128,7 @@ __global__ void ce_row_bf16_kernel(const float* __restrict__ logits, int V, cons
   if (threadIdx.x == 0 && row_loss) row_loss[r] = lse - z[tgt];
   if (dlogits) {
     const float sc = (gscale ? gscale[0] : 1.f) * inv_rows;
-    __nv_bfloat16* d = dlogits + r * V;
+    __nv_bfloat16* d = dlogits + omap(r);
     if ((V & 3) == 0) {
       const float4* z4 = reinterpret_cast<const float4*>(z);
       for (int j = threadIdx.x; j < V / 4; j += blockDim.x) {
@@ -261,7 +261,26 @@ extern "C" int s2vt_ce_bf16(void* stream, const float* logits, int64_t R, int V,
   S2VT_REQUIRE(!have_lse || row_lse, "s2vt_ce_bf16: have_lse needs row_lse");
   cudaStream_t st = (cudaStream_t)stream;
   ce_row_bf16_kernel<<<(unsigned)R, 256, 0, st>>>(logits, V, targets, to_rowmap(tmap), row_loss, row_lse, have_lse,
-                                                 (__nv_bfloat16*)dlogits_bf16, gscale, 1.0f / (float)R);
+                                                 (__nv_bfloat16*)dlogits_bf16, gscale, 1.0f / (float)R, RowMap{1, (long long)V, 0});
+  S2VT_CHECK_LAUNCH();
+  if (loss) {
+    mean_f32_kernel<<<1, 256, 0, st>>>(row_loss, R, loss);
+    S2VT_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int s2vt_ce_bf16_mapped(void* stream, const float* logits, int64_t R, int V, const int64_t* targets, s2vt_rowmap tmap,
+                                   float* row_loss, float* loss, float* row_lse, int have_lse, void* dlogits_bf16, s2vt_rowmap omap,
+                                   const float* gscale) {
+  S2VT_REQUIRE(logits && targets, "s2vt_ce_bf16_mapped: null pointer");
+  S2VT_REQUIRE(R > 0 && V > 0, "s2vt_ce_bf16_mapped: empty input");
+  S2VT_REQUIRE(!loss || row_loss, "s2vt_ce_bf16_mapped: loss needs row_loss scratch");
+  S2VT_REQUIRE(!have_lse || row_lse, "s2vt_ce_bf16_mapped: have_lse needs row_lse");
+  S2VT_REQUIRE(omap.inner >= 1 && tmap.inner >= 1, "s2vt_ce_bf16_mapped: rowmap.inner must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  ce_row_bf16_kernel<<<(unsigned)R, 256, 0, st>>>(logits, V, targets, to_rowmap(tmap), row_loss, row_lse, have_lse,
+                                                 (__nv_bfloat16*)dlogits_bf16, gscale, 1.0f / (float)R, to_rowmap(omap));
   S2VT_CHECK_LAUNCH();
   if (loss) {
     mean_f32_kernel<<<1, 256, 0, st>>>(row_loss, R, loss);

@@ -11,4 +11,8 @@ static inline int read_sm100_error_flag() {
   if (cudaMemcpyFromSymbol(&v, g_sm100_error, sizeof(int)) != cudaSuccess) return -3;
   return v;
 }
+static inline int clear_sm100_error_flag() {
+  const int z = 0;
+  return cudaMemcpyToSymbol(g_sm100_error, &z, sizeof(int)) == cudaSuccess ? 0 : -3;
+}
 }  // namespace s2vt

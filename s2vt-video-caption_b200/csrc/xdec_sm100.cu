@@ -854,6 +854,7 @@ int make_tmap_planes(CUtensorMap* out, const void* base, uint64_t k, uint64_t ro
 }
 
 int xdec_error_flag() { return read_sm100_error_flag(); }
+int xdec_error_clear() { return clear_sm100_error_flag(); }
 
 }  // namespace s2vt
 

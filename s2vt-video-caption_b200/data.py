@@ -59,21 +59,32 @@ class DeviceFeatureStore:
             mask[r, :len(label)] = 1.0
         return torch.from_numpy(pad).to(self.device, non_blocking=True), torch.from_numpy(mask).to(self.device, non_blocking=True)
 
-    def batch(self, indices: Sequence[int]):
-        """(feats [B,L,F], pad_label [B,L] int64, IDs list[str], mask [B,L]) -- what a DataLoader yields over VideoDataset items."""
+    def batch(self, indices: Sequence[int], into=None):
+        """(feats [B,L,F], pad_label [B,L] int64, IDs list[str], mask [B,L]) -- what a DataLoader yields over VideoDataset items.
+        `into`: a dp.DataParallelTrainer -- features and labels are gathered straight into its static input buffers, so its
+        captured train step replays without an extra copy."""
         idx = torch.as_tensor(list(indices), dtype=torch.int64, device=self.device)
+        pad, mask = self._labels(indices)
+        if into is not None and not self.feats_require_grad and self.feats.is_cuda:
+            fb, tb = into.input_buffers((len(indices),) + tuple(self.feats.shape[1:]), tuple(pad.shape), self.feats.dtype)
+            torch.index_select(self.feats, 0, idx, out=fb)
+            tb.copy_(pad, non_blocking=True)
+            return fb, tb, [self.ids[i] for i in indices], mask
         feats = self.feats.index_select(0, idx)
         if self.feats_require_grad:
             feats.requires_grad_(True)
-        pad, mask = self._labels(indices)
         return feats, pad, [self.ids[i] for i in indices], mask
 
-    def batches(self, batch_size: int, shuffle: bool = False, generator: Optional[torch.Generator] = None) -> Iterator:
-        """One pass over the split (train.py:62-65: shuffle=True for training, False for validation / test)."""
+    def batches(self, batch_size: int, shuffle: bool = False, generator: Optional[torch.Generator] = None, into=None,
+                only: Optional[Tuple[int, int, int]] = None) -> Iterator:
+        """One pass over the split (train.py:62-65: shuffle=True for training, False for validation / test).
+        `only` = (rank, world, usable): yield only batches rank, rank+world, ... of the first `usable` (data-parallel fit())."""
         n = len(self)
         order = torch.randperm(n, generator=generator).tolist() if shuffle else list(range(n))
-        for s in range(0, n, batch_size):
-            yield self.batch(order[s:s + batch_size])
+        for bi, s in enumerate(range(0, n, batch_size)):
+            if only is not None and (bi >= only[2] or bi % only[1] != only[0]):
+                continue
+            yield self.batch(order[s:s + batch_size], into=into)
 
     def shard(self, rank: int, world: int) -> List[int]:
         """Contiguous item shard of this rank (beam / greedy evaluation shards videos, no collective on the path)."""

@@ -159,6 +159,13 @@ class DataParallelTrainer:
         self.max_graphs = 8
         self._adam_stream = None
         self._execs: List[int] = []
+        # A captured step is tied to the addresses of its inputs.  Batches from a loader live in fresh tensors every step, so the
+        # trainer owns one static (feats, targets) pair per input shape: step() copies the batch in (or the loader gathers straight
+        # into input_buffers()) and replays that pair's graph.  Buffers passed to register_inputs() are replayed in place.
+        self._static: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._registered: set = set()
+        self.replays = 0
+        self.steps_since_check = 0
 
     def __del__(self):
         try:
@@ -171,6 +178,8 @@ class DataParallelTrainer:
     def _bucket_ready(self, bucket: str) -> None:
         """Called by backward once every kernel producing `bucket`'s gradients has been enqueued (and nothing later in the step
         reads that bucket's weights): all-reduce it, then update it, both beside the rest of backward."""
+        if not (self.opt._flat or {}).get("active"):
+            return               # a plain loss.backward() outside trainer.step(): FusedAdam.step() gathers and steps everything itself
         self.reducer.ready(bucket)
         if not self.early_adam:
             return
@@ -190,11 +199,57 @@ class DataParallelTrainer:
             self.opt.step_range(a, b)
             self.opt.refresh_derived(bucket)
 
+    # ---- input buffers
+    def input_buffers(self, feats_shape, targets_shape, dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The trainer-owned (feats, targets) pair for this input shape; a loader that fills these and passes them to step() pays no
+        copy (data.DeviceFeatureStore.batches(into=...))."""
+        key = (tuple(feats_shape), dtype, tuple(targets_shape))
+        ent = self._static.get(key)
+        if ent is None:
+            dev = self.reducer.flat.device
+            ent = (torch.empty(feats_shape, dtype=dtype, device=dev), torch.empty(targets_shape, dtype=torch.int64, device=dev))
+            self._static[key] = ent
+            self._registered.add((ent[0].data_ptr(), ent[1].data_ptr()))
+        return ent
+
+    def register_inputs(self, feats: torch.Tensor, targets: torch.Tensor) -> None:
+        """Declare a caller-owned, long-lived (feats, targets) pair (e.g. double buffers behind an H2D copy stream): steps on it are
+        captured and replayed in place, without the copy into the trainer's own buffers.  At most `max_graphs` pairs."""
+        self._registered.add((feats.data_ptr(), targets.data_ptr()))
+
+    def release_graphs(self) -> None:
+        """Drop every captured step (they hold NCCL kernels when world > 1): call before dist.destroy_process_group()."""
+        if self._graphs:
+            torch.cuda.synchronize()
+        self._graphs.clear()
+        self._registered.clear()
+        self._static.clear()
+        self._pool = None
+        from .lib import load
+        for e in self._execs:
+            load().s2vt_graph_exec_destroy(e)
+        self._execs = []
+
+    def check_device_errors(self) -> None:
+        """Synchronises and raises if a tensor-core kernel flagged a lost barrier arrival (sm100_ptx.cuh: a wait that gives up after
+        2 s sets a sticky flag and the kernel carries on with garbage).  fit() / validate() call this once per epoch."""
+        from .lib import load, S2VTLibraryError
+        self.steps_since_check = 0
+        code = load().s2vt_device_error_flag(None)
+        if code != 0:
+            load().s2vt_device_error_clear()
+            raise S2VTLibraryError("a tensor-core kernel reported a timed-out barrier wait (code %d): the results of the steps since the "
+                                   "last check are not trustworthy" % code)
+
     def _step_eager(self, feats, targets, mask=None):
         self.opt.zero_grad(set_to_none=True)
         loss = self.model.forward_loss(feats, targets, mask)
         self.opt.begin_step()
         loss.backward()
+        # backward normally writes each gradient straight into the optimizer's flat buffer (and fires the bucket callbacks); when it
+        # could not (a frozen parameter, a device mismatch) autograd produced ordinary .grad tensors: bring them into the flat buffer
+        # before it is reduced and stepped, instead of training on whatever the buffer held
+        self.opt.gather_grads()
         self.reducer.finish()
         if self._adam_stream is not None:
             torch.cuda.current_stream(self.reducer.flat.device).wait_stream(self._adam_stream)
@@ -215,12 +270,19 @@ class DataParallelTrainer:
         if f.get("shadow_state") != (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"])) or not f.get("derived_ok"):
             self._eager_steps += 1
             return self._step_eager(feats, targets, mask)
-        key = (feats.data_ptr(), targets.data_ptr(), tuple(feats.shape), tuple(targets.shape), feats.requires_grad, feats.dtype)
+        if self._eager_steps < 2 or feats.requires_grad:         # (feats.grad belongs to the caller's tensor: no static copy of it)
+            self._eager_steps += 1
+            return self._step_eager(feats, targets, mask)
+        if (feats.data_ptr(), targets.data_ptr()) not in self._registered or \
+                (len(self._graphs) >= self.max_graphs and
+                 (feats.data_ptr(), targets.data_ptr(), tuple(feats.shape), tuple(targets.shape), False, feats.dtype) not in self._graphs):
+            sf, st_ = self.input_buffers(feats.shape, targets.shape, feats.dtype)
+            sf.copy_(feats, non_blocking=True)
+            st_.copy_(targets, non_blocking=True)
+            feats, targets = sf, st_
+        key = (feats.data_ptr(), targets.data_ptr(), tuple(feats.shape), tuple(targets.shape), False, feats.dtype)
         ent = self._graphs.get(key)
         if ent is None:
-            if self._eager_steps < 2 or len(self._graphs) >= self.max_graphs:
-                self._eager_steps += 1
-                return self._step_eager(feats, targets, mask)
             ent = self._capture(key, feats, targets, mask)
         graph, loss, n_launch, _keep, exec_ = ent
         self.opt.sync_lr()
@@ -231,6 +293,7 @@ class DataParallelTrainer:
             graph.replay()
         self.opt.note_replayed_step()
         load().s2vt_add_launch_count(n_launch)
+        self.replays += 1
         return loss
 
     def _capture(self, key, feats, targets, mask):

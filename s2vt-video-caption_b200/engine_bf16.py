@@ -142,12 +142,14 @@ def colsum_bf16(X, M, N, ld, out, out2=None, x_off=0):
     L.check(rc, "s2vt_colsum_bf16")
 
 
-def ce_bf16(logits, R, V, targets, t_off, tmap, loss=None, dlogits=None, gscale=None, row_lse=None, have_lse=False):
+def ce_bf16(logits, R, V, targets, t_off, tmap, loss=None, dlogits=None, gscale=None, row_lse=None, have_lse=False, omap=None):
+    """omap: row map of the bf16 gradient (default: dense rows in logits order)."""
     row_loss = torch.empty(R, dtype=torch.float32, device=logits.device) if loss is not None else None
     with ops._timed("ce_bf16", 0.0, 4.0 * R * V + (2.0 * R * V if dlogits is not None else 0.0)):
-        rc = L.load().s2vt_ce_bf16(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
-                                   L.ptr(loss), L.ptr(row_lse), int(have_lse), L.ptr(dlogits), L.ptr(gscale))
-    L.check(rc, "s2vt_ce_bf16")
+        rc = L.load().s2vt_ce_bf16_mapped(L.stream_ptr(logits.device), L.ptr(logits), R, V, L.ptr(targets, t_off), tmap, L.ptr(row_loss),
+                                          L.ptr(loss), L.ptr(row_lse), int(have_lse), L.ptr(dlogits), omap if omap is not None else dense(V),
+                                          L.ptr(gscale))
+    L.check(rc, "s2vt_ce_bf16_mapped")
 
 
 # ------------------------------------------------------------------------------------------------ bf16 weight shadows

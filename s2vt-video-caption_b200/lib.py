@@ -44,6 +44,7 @@ SIGNATURES = {
     "s2vt_adam_f32_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _vp, _f, _vp]),
     "s2vt_has_tcgen05": (_i, []),
     "s2vt_device_error_flag": (_i, [_vp]),
+    "s2vt_device_error_clear": (_i, []),
     "s2vt_gemm_f32": (_i, [_vp, _i, _i, _i, _vp, RowMap, _i, _vp, RowMap, _i, _vp, RowMap, _vp, _i, _i, _i64]),
     "s2vt_gemm_bf16": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, RowMap, _i, _vp, _i]),
     "s2vt_gemm_bf16_set_mode": (_i, [_i, _i]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "s2vt_embed_gather_bf16": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64]),
     "s2vt_colsum_bf16": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp]),
     "s2vt_ce_bf16": (_i, [_vp, _vp, _i64, _i, _vp, RowMap, _vp, _vp, _vp, _i, _vp, _vp]),
+    "s2vt_ce_bf16_mapped": (_i, [_vp, _vp, _i64, _i, _vp, RowMap, _vp, _vp, _vp, _i, _vp, RowMap, _vp]),
     "s2vt_bcast_rows_f32": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "s2vt_vocab_ce_ws_bytes": (_i64, [_i, _i]),
     "s2vt_vocab_ce_fwd_bf16": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, RowMap, _vp, _vp, _vp, _vp, _vp]),

@@ -12,6 +12,7 @@ anything else raises NotImplementedError -- there is no cuDNN / CPU fallback on 
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -333,6 +334,20 @@ class _TrainLossFn(torch.autograd.Function):
         return (None, dfeats, None) + _finish_grads(ctx.module, direct, grads)
 
 
+# forward(mode='train') hands fp32 logits to the caller; when the caller's loss is this package's MaskCriterion, its backward
+# looks the producer up here (by the logits' address) and leaves dL/dlogits for it as time-major bf16 -- what the backward GEMMs
+# read -- instead of a 263 MB fp32 tensor that would have to be transposed and cast again.
+_LOGITS_PRODUCERS: Dict[int, "weakref.ref"] = {}
+
+
+def lookup_logits_producer(logits2d: torch.Tensor):
+    ref = _LOGITS_PRODUCERS.get(logits2d.data_ptr())
+    ctx = ref() if ref is not None else None
+    if ctx is None or getattr(ctx, "logits_numel", -1) != logits2d.numel():
+        return None
+    return ctx
+
+
 class _TrainLogitsBf16Fn(torch.autograd.Function):
     """forward(mode='train') on tensor cores -> materialised fp32 logits [B,L-1,V] (the API contract); backward receives
     dL/dlogits from autograd (e.g. from MaskCriterion), casts it to bf16 in time-major order and runs the bf16 BPTT."""
@@ -344,13 +359,26 @@ class _TrainLogitsBf16Fn(torch.autograd.Function):
         ctx.S = module._shadow.get(P, getattr(module, '_adam_shadow', None))
         logits, saved = EB.train_forward(P, ctx.S, feats, targets, stash=need, batch_major_logits=True)
         ctx.saved, ctx.P, ctx.targets, ctx.module = saved, P, targets, module
+        ctx.dl_bf16, ctx.logits_numel = None, logits.numel()
+        if need:
+            if len(_LOGITS_PRODUCERS) > 64:
+                for k in [k for k, r in _LOGITS_PRODUCERS.items() if r() is None]:
+                    del _LOGITS_PRODUCERS[k]
+            _LOGITS_PRODUCERS[logits.data_ptr()] = weakref.ref(ctx)
         return logits
 
     @staticmethod
     def backward(ctx, dl):
         B, Lm1, V = dl.shape
-        # [B, L-1, V] f32 -> time-major [(L-1)B, V] bf16 (layout glue for the caller-supplied gradient)
-        dl_tm = dl.transpose(0, 1).contiguous().view(Lm1 * B, V).to(torch.bfloat16)
+        fused = ctx.dl_bf16                     # left here by MaskCriterion's backward (time-major bf16), or None
+        ctx.dl_bf16 = None
+        if fused is not None and all(st == 0 for st in dl.stride()):
+            dl_tm = fused                       # `dl` is MaskCriterion's zero-stride placeholder: nothing else contributed
+        else:
+            # a caller-supplied gradient: [B, L-1, V] f32 -> time-major [(L-1)B, V] bf16
+            dl_tm = dl.transpose(0, 1).contiguous().view(Lm1 * B, V).to(torch.bfloat16)
+            if fused is not None:
+                dl_tm = dl_tm + fused
         direct, cb = _direct_grad_targets(ctx.module)
         G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
         ctx.saved = None

@@ -17,8 +17,31 @@ class FusedAdam(torch.optim.Optimizer):
     the data-parallel all-reduce works on contiguous bucket slices."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
-        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
+        params = list(params)
+        if params and isinstance(params[0], dict) and len(params) > 1:
+            raise ValueError("FusedAdam keeps one flat buffer with one set of hyper-parameters: pass a single parameter group "
+                             "(the reference uses Adam(model.parameters(), lr), train.py:89)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._flat = None
+
+    # m, v and the step count live in the flat buffers, not in self.state: carry them through (load_)state_dict explicitly
+    def state_dict(self):
+        sd = super().state_dict()
+        f = self._flat
+        if f is not None:
+            sd["fused"] = {"step": int(f["step"]), "m": f["m"].clone(), "v": f["v"].clone()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        fused = state_dict.get("fused")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "fused"})
+        if fused is not None:
+            f = self._ensure_flat()
+            if fused["m"].numel() != f["m"].numel():
+                raise ValueError("FusedAdam.load_state_dict: flat state has %d elements, this optimizer %d" % (fused["m"].numel(), f["m"].numel()))
+            f["m"].copy_(fused["m"]); f["v"].copy_(fused["v"]); f["step"] = int(fused["step"])
+            if "step_dev" in f:
+                f["step_dev"].fill_(f["step"])
 
     def _ensure_flat(self):
         if self._flat is not None:
@@ -101,10 +124,28 @@ class FusedAdam(torch.optim.Optimizer):
             f["lr_host"] = lr
 
     @torch.no_grad()
+    def gather_grads(self) -> int:
+        """Copies every parameter's .grad that is not already a view of the flat gradient buffer into it (zero for a parameter
+        without a gradient: its update is then pure momentum decay -- zero for a parameter that never had one).  Returns how many
+        tensors had to be copied; 0 on the normal path where backward wrote in place."""
+        f = self._ensure_flat()
+        moved = 0
+        for p, o in zip(f["params"], f["offsets"]):
+            gv = f["g"][o:o + p.numel()].view(p.shape)
+            if p.grad is None:
+                gv.zero_()
+                moved += 1
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)
+                moved += 1
+        return moved
+
+    @torch.no_grad()
     def begin_step(self) -> None:
         f = self._ensure_flat()
         f["step"] += 1
         f["stepped"] = []
+        f["active"] = True                      # bucket callbacks arriving outside begin_step()..finish_step() are ignored (dp.py)
         if "step_dev" in f:
             if not torch.cuda.is_current_stream_capturing():
                 self.sync_lr()
@@ -162,6 +203,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self.step_range(pos, a, grad_scale)
             pos = max(pos, b)
         f["stepped"] = []
+        f["active"] = False
         f["shadow_state"] = (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"]))
         f["derived_ok"] = f.pop("derived_done", set()) == {"vid_rnn", "word_rnn"}     # (a replayed graph repeats what its capture did)
 

@@ -36,6 +36,9 @@ CASES = {
                  eos_bias=0.0, full=False, beams=(3, 5), beam_videos=2),
     "msvd_peaky": dict(V=13000, F=4096, H=512, E=512, L=80, B=4, real=28, wseed=5, dseed=77, out_scale=40.0,
                        eos_bias=3.0, full=False, beams=(3,), beam_videos=2),
+    # BASELINE configs[1], the benched configuration: batch 64, plus a 5-step Adam trajectory over 5 different batches
+    "c2": dict(V=13000, F=4096, H=512, E=512, L=80, B=64, real=28, wseed=0, dseed=4000, out_scale=1.0,
+               eos_bias=0.0, full=False, beams=(), beam_videos=0, adam_steps=5),
     "paper": dict(V=5000, F=2048, H=1000, E=500, L=80, B=2, real=28, wseed=31, dseed=32, out_scale=1.0,
                   eos_bias=0.0, full=False, beams=(), beam_videos=0),
 }
@@ -100,6 +103,28 @@ def run_case(name, c):
         for k, p in model.named_parameters():
             out["adam1/" + k] = p.detach().numpy().copy()
         model = build_reference(c, P)                        # restore weights for beam search
+        model.eval()
+    # N-step training trajectory (train.py:116-127 with Adam lr=1e-4): loss before every step, sampled weights after the last
+    if c.get("adam_steps"):
+        model = build_reference(c, P)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        losses = []
+        for i in range(c["adam_steps"]):
+            f_i, t_i, m_i = O.synth_batch(c["B"], c["L"], c["F"], c["V"], seed=c["dseed"] + i, real_tokens=c["real"])
+            opt.zero_grad()
+            lg_i = model(torch.from_numpy(f_i).requires_grad_(True), targets=torch.from_numpy(t_i)[:, :-1], mode="train")
+            l_i = crit(lg_i, torch.from_numpy(t_i), torch.from_numpy(m_i))
+            l_i.backward()
+            opt.step()
+            losses.append(l_i.item())
+        out["traj_loss"] = np.asarray(losses, np.float64)
+        for k, p in model.named_parameters():
+            v = p.detach().numpy()
+            out["traj_param_sample/" + k] = sample(v)
+            out["traj_delta_norm/" + k] = np.float64(np.linalg.norm((v - P[k]).astype(np.float64)))
+        out["cfg_adam_steps"] = np.asarray(c["adam_steps"])
+        model = build_reference(c, P)
         model.eval()
     for bw in c["beams"]:
         nv = c["beam_videos"]

@@ -391,8 +391,13 @@ def test_bf16_train_step_vs_reference_golden(dev):
         n = np.linalg.norm(gv.astype(np.float64))
         nrel = abs(n - float(g["grad_norm/" + k])) / float(g["grad_norm/" + k])
         print("grad %-24s rel-L2 err (sampled) %.3e   norm rel err %.3e" % (k, rel, nrel))
-        assert rel <= 5e-2, k
-        assert nrel <= 2e-2, k
+        assert rel <= 1e-2, k                 # observed 4e-3 .. 6e-3
+        assert nrel <= 1e-2, k
+    # The error floor of ANY design whose products take bf16 operands, measured on the CPU by rounding operands only
+    # (tools/bf16_error_budget.py, profiles/r02_bf16_error_budget.txt): weights + inputs 1.71e-3, + h_t 1.88e-3, + other activations
+    # 1.92e-3 (= 0.016 sigma_z).  SURVEY 8(c)'s "1e-3 sigma" (1.2e-4) is below that floor; what the kernels may add on top
+    # (tanh.approx, ex2.approx, summation order) is held to 20 % of it.
+    assert np.abs(ls - ref).max() <= 1.2 * 1.915e-3
 
 
 def test_bf16_fused_loss_matches_api_path(dev):
@@ -474,3 +479,143 @@ def test_bf16_feature_store_batches_match_float32_batches(dev):
         model(feats.to(torch.bfloat16), mode="test")
     with pytest.raises(ValueError):
         model.forward_loss(feats.to(torch.bfloat16).requires_grad_(True), targets)
+
+
+# ------------------------------------------------------------------ the benched configuration (BASELINE configs[1]) vs the reference
+def test_c2_batch64_trajectory_through_trainer_with_graph_replay(dev):
+    """tests/golden/c2.npz: the unmodified reference at B=64 (loss, sampled gradients, and a 5-step Adam trajectory over five
+    different batches).  Here the same five batches go through DataParallelTrainer.step() as fresh tensors, i.e. through the
+    trainer's static input buffers and, from the third step on, CUDA-graph replay -- the path bench.py times."""
+    from conftest import golden_cfg, load_golden
+    from oracle import s2vt_numpy as O
+    from s2vt_b200.dp import DataParallelTrainer
+    g = load_golden("c2")
+    c = golden_cfg(g)
+    P = O.synth_params(c["V"], c["F"], c["H"], c["E"], seed=c["wseed"], out_scale=c["out_scale"], eos_bias=c["eos_bias"])
+    model = s2vt_b200.S2VT(c["V"], c["F"], c["L"], dim_hid=c["H"], dim_embed=c["E"], train_precision="bf16")
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in P.items()}, strict=True)
+    model = model.to(dev)
+    # (1) loss and gradients of the first batch, fused path
+    f0, t0, m0 = O.synth_batch(c["B"], c["L"], c["F"], c["V"], seed=c["dseed"], real_tokens=c["real"])
+    loss = model.forward_loss(torch.from_numpy(f0).to(dev), torch.from_numpy(t0).to(dev))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-3 * float(g["loss"])
+    for k, p in model.named_parameters():
+        gv = p.grad.detach().cpu().numpy()
+        rs = g["grad_full/" + k].reshape(-1) if "grad_full/" + k in g else g["grad_sample/" + k]
+        gs = gv.reshape(-1) if "grad_full/" + k in g else gv.reshape(-1)[::997]
+        rel = np.linalg.norm(gs.astype(np.float64) - rs) / max(1e-30, np.linalg.norm(rs.astype(np.float64)))
+        assert rel <= 1e-2, (k, rel)
+        p.grad = None
+    del loss        # (its autograd graph pins the parameters' AccumulateGrad nodes to this stream; a later graph capture must not meet them)
+    # (2) five training steps, fresh tensors every step
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-4)
+    tr = DataParallelTrainer(model, opt, cuda_graph=True)
+    losses = []
+    for i in range(int(c["adam_steps"])):
+        f_i, t_i, _ = O.synth_batch(c["B"], c["L"], c["F"], c["V"], seed=c["dseed"] + i, real_tokens=c["real"])
+        losses.append(float(tr.step(torch.from_numpy(f_i).to(dev), torch.from_numpy(t_i).to(dev)).item()))
+    torch.cuda.synchronize()
+    assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+    assert tr.replays >= 3 and len(tr._graphs) == 1
+    print("\nc2 trajectory loss: ours", ["%.5f" % x for x in losses], " reference", ["%.5f" % x for x in g["traj_loss"]])
+    for a, b in zip(losses, g["traj_loss"]):
+        assert abs(a - b) <= 1e-3 * abs(b), (losses, g["traj_loss"])
+    worst = 0.0
+    for k, p in model.named_parameters():
+        pv = p.detach().cpu().numpy()
+        d_ours = pv.reshape(-1)[::997].astype(np.float64) - P[k].reshape(-1)[::997]
+        d_ref = g["traj_param_sample/" + k].astype(np.float64) - P[k].reshape(-1)[::997]
+        rel = np.linalg.norm(d_ours - d_ref) / max(1e-30, np.linalg.norm(d_ref))
+        nrm = np.linalg.norm((pv - P[k]).astype(np.float64))
+        nrel = abs(nrm - float(g["traj_delta_norm/" + k])) / float(g["traj_delta_norm/" + k])
+        print("5-step update %-24s rel-L2 err of the sampled update %.3e   update-norm rel err %.3e" % (k, rel, nrel))
+        worst = max(worst, rel)
+        # Adam's first steps move every weight by ~lr * sign-like(g): an element whose tiny gradient changes sign under bf16 rounding
+        # moves the other way, so the update agrees in norm much more tightly than element by element
+        assert rel <= 0.25, (k, rel)
+        assert nrel <= 2e-2, (k, nrel)
+
+
+def test_fresh_batches_replay_one_graph_per_shape(dev):
+    """What fit() does: a loader yields freshly allocated batches (two shapes: full and tail).  The trainer must replay, not
+    re-capture per pointer (round-1 defect: graphs were keyed on data_ptr and never replayed under fit())."""
+    from s2vt_b200.dp import DataParallelTrainer
+    V, F, H, E, Lq = 136, 64, 128, 64, 6
+    torch.manual_seed(5)
+    model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-3)
+    tr = DataParallelTrainer(model, opt, cuda_graph=True)
+    ref_model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    ref_model.load_state_dict(model.state_dict())
+    ref_opt = s2vt_b200.FusedAdam(ref_model.parameters(), lr=1e-3)
+    ref_tr = DataParallelTrainer(ref_model, ref_opt, cuda_graph=False)
+    g = torch.Generator().manual_seed(9)
+    first = last = None
+    for i in range(50):
+        B = 5 if i % 10 == 9 else 8                       # a tail batch now and then
+        feats = torch.randn(B, Lq, F, generator=g).to(dev)
+        targets = torch.randint(0, V, (B, Lq), generator=g).to(dev)
+        last = float(tr.step(feats, targets).item())
+        ref_last = float(ref_tr.step(feats.clone(), targets.clone()).item())
+        assert abs(last - ref_last) <= 2e-3 * abs(ref_last), (i, last, ref_last)
+        first = last if first is None else first
+    assert len(tr._graphs) <= 2 and tr.replays >= 45, (len(tr._graphs), tr.replays)
+    assert last < first
+    tr.check_device_errors()
+    # zero-copy route: a loader that fills the trainer's own buffers
+    fb, tb = tr.input_buffers((8, Lq, F), (8, Lq))
+    fb.normal_(); tb.random_(0, V)
+    n = tr.replays
+    tr.step(fb, tb)
+    assert tr.replays == n + 1 and len(tr._graphs) <= 2
+
+
+def test_frozen_parameter_still_trains_the_others(dev):
+    """with one tensor frozen backward falls back to ordinary autograd gradients; the trainer must bring them into
+    the flat buffer instead of stepping on stale zeros."""
+    from s2vt_b200.dp import DataParallelTrainer
+    V, F, H, E, Lq, B = 136, 64, 128, 64, 6, 4
+    torch.manual_seed(6)
+    model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    model.embedding.weight.requires_grad_(False)
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-3)
+    tr = DataParallelTrainer(model, opt, cuda_graph=False)
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(B, Lq, F, generator=g).to(dev)
+    targets = torch.randint(0, V, (B, Lq), generator=g).to(dev)
+    l0 = float(tr.step(feats, targets).item())
+    for _ in range(5):
+        l1 = float(tr.step(feats, targets).item())
+    assert l1 < l0
+    assert torch.equal(model.embedding.weight, before["embedding.weight"])
+    assert not torch.equal(model.out_linear.weight, before["out_linear.weight"])
+
+
+def test_fused_adam_state_dict_roundtrip(dev):
+    V, F, H, E, Lq, B = 136, 64, 128, 64, 6, 4
+    torch.manual_seed(7)
+    model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E).to(dev)
+    opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(2)
+    feats = torch.randn(B, Lq, F, generator=g).to(dev)
+    targets = torch.randint(0, V, (B, Lq), generator=g).to(dev)
+    for _ in range(3):
+        opt.zero_grad()
+        model.forward_loss(feats, targets).backward()
+        opt.step()
+    sd = opt.state_dict()
+    assert sd["fused"]["step"] == 3 and float(sd["fused"]["v"].abs().sum()) > 0
+    model2 = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E).to(dev)
+    model2.load_state_dict(model.state_dict())
+    opt2 = s2vt_b200.FusedAdam(model2.parameters(), lr=1e-3)
+    opt2.load_state_dict(sd)
+    for o, m in ((opt, model), (opt2, model2)):
+        o.zero_grad()
+        m.forward_loss(feats, targets).backward()
+        o.step()
+    for (k, a), (_, b) in zip(model.named_parameters(), model2.named_parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-7), k
+    with pytest.raises(ValueError):
+        s2vt_b200.FusedAdam([{"params": [model.embedding.weight]}, {"params": [model.out_linear.weight], "lr": 1e-2}])
