@@ -311,11 +311,11 @@ def gpu_incumbent_run(dev, B):
 # ------------------------------------------------------------------------------------------- decode (greedy / beam) on this rank's videos
 def decode_run(s2vt_b200, dev, rank, world, sync_all, peaks):
     """BASELINE metric, second half: greedy and beam-5 captions/s.  Every rank decodes its own synthetic videos (weak scaling; no
-    collective on the path): 1024 videos greedy in batches of 512, 512 videos beam-5 in batches of 256, features resident in HBM;
+    collective on the path): 1024 videos greedy in batches of 512, 460 videos beam-5 in batches of 230, features resident in HBM;
     `e2e` adds the H2D copy of the features from pinned host memory and the D2H read of the token ids."""
     torch.manual_seed(0)
     model = s2vt_b200.S2VT(CFG["V"], CFG["F"], CFG["L"], dim_hid=CFG["H"], dim_embed=CFG["E"]).to(dev).eval()
-    GB, NG, BB, NB = 512, 1024, 256, 512
+    GB, NG, BB, NB = 512, 1024, 230, 460      # beam: 230 videos x 5 beams = 1150 slots = 9 row tiles -> the step kernels are one wave (144 CTAs)
     g = torch.Generator().manual_seed(99 + rank)
     host = torch.randn(NG, CFG["L"], CFG["F"], generator=g).pin_memory()
     feats = host.to(dev)

@@ -364,8 +364,10 @@ int64_t s2vt_xdec_greedy_ws_bytes(s2vt_xdec_cfg cfg, int B);
 int s2vt_xdec_greedy(void* stream, s2vt_xdec_cfg cfg, const void* wbuf, int B, const float* feats, int64_t* tokens, void* ws);
 
 /* S2VT.forward(mode='beam_search'), S2VTModel.py:56-61,149-240, lock-step over videos x beams (same outputs as
- * s2vt_beam_search_f32).  beam_width <= 8.  check_every > 0: the host reads the number of finished videos every that many
- * depths (one stream sync each) and stops early when all are; host_flag: pinned int32 for that read (may be NULL if 0). */
+ * s2vt_beam_search_f32).  beam_width <= 8.  check_every > 0: every that many depths the number of finished videos is copied
+ * to pinned host memory; the host looks at the PREVIOUS chunk's count before enqueuing the next chunk and stops when every video has
+ * finished (the stream never drains; at most one chunk of depths runs past the end, changing nothing).
+ * host_flag: pinned int32[4] for those reads (may be NULL if check_every == 0). */
 int64_t s2vt_xdec_beam_ws_bytes(s2vt_xdec_cfg cfg, int B, int beam_width, int max_depth);
 int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf, int B, const float* feats, int beam_width, int max_depth,
                    int topk, const float* len_pen, int64_t* out_tokens, int32_t* out_len, void* ws, int check_every,

@@ -64,6 +64,8 @@ struct XParams {
   __half* hp; long long hp_ld; long long hp_plane;             // h planes (scale 2^15)
   // BEAM partial outputs (two per tile: one per epilogue warp group)
   float* o_val; int* o_idx; float* o_ms;
+  unsigned int* row_thr; int kc;                               // BEAM: [M][KC] per-row slot maxima (order_f32 bits, 0 = none yet)
+  int m_fastest;                                               // grid is (row tiles, column tiles) instead of (column tiles, row tiles)
   unsigned long long* o_key;                                   // ARGMAX: per-row packed (value, index) maximum, zeroed by the consumer
   // LSTM: the previous step's argmax keys -> token (gidx == nullptr); n-tile 0 records it and clears the keys of the next step
   const unsigned long long* key_in; unsigned long long* key_clear; int64_t* tok_out; long long tok_ld;
@@ -86,6 +88,14 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// order-preserving map float -> uint32 (0 is below every float) and back
+__device__ __forceinline__ uint32_t order_f32(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
 __device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
   const uint32_t b = __float_as_uint(v);
   const uint32_t u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -117,10 +127,13 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, int nmain, uint32_t (&r
   for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(256, 1)
+// MINB = 2: two CTAs share an SM (64-column tiles, a 2-stage ring of 96 KB and 256 TMEM columns each), so that one CTA's epilogue
+// runs under the other's tile loads and MMAs.  Measured on the beam vocab product: slower than one CTA with 128-column tiles
+// (225 vs 191 us per depth: the epilogue's cost is per row, not per column), so no caller uses it at present.
+template <int BN, int EPI, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const XParams p) {
-  constexpr int STAGES = (BN == 128) ? 3 : 4;
+  constexpr int STAGES = (MINB == 2) ? 2 : ((BN == 128) ? 3 : 4);
   constexpr int PLANE_B = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;
   extern __shared__ uint8_t smem_raw[];
@@ -130,7 +143,11 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // row-tile-fastest grids (vocab products of the beam step): CTAs that run together cover all row tiles of a few column tiles, so
+  // a row's later column tiles see the candidate threshold its earlier ones published
+  const int tile_m = p.m_fastest ? blockIdx.x : blockIdx.y, tile_n = p.m_fastest ? blockIdx.y : blockIdx.x;
+  const int n_tiles = p.m_fastest ? gridDim.y : gridDim.x;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
   unsigned long long* const trace = (p.trace && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = ptx::globaltimer_ns();
 
@@ -251,7 +268,7 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.gidx) tok = p.gidx[m];
         else {
           tok = key_index(__ldcg(p.key_in + m));
-          if (blockIdx.x == 0 && half == 0) {
+          if (tile_n == 0 && half == 0) {
             if (p.tok_out) p.tok_out[(long long)m * p.tok_ld] = tok;
             if (p.key_clear) p.key_clear[m] = 0ull;
           }
@@ -361,11 +378,21 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // highest value and, among equal values, the lowest index (torch.argmax)
       if (row_ok && bi != 0x7fffffff) atomicMax(p.o_key + m, pack_key(bv, bi));
     } else {   // EPI_BEAM
+      // Per (row, tile half): running max / sum exp of the logits and the best KC candidates.  Every tile half publishes its maximum
+      // into one of kc per-row slots (slot = part % kc, atomicMax): the slots hold kc DIFFERENT elements of the row, so their minimum is
+      // a lower bound of the row's kc-th best logit, and a candidate below it is skipped (>=: an equal value may still win on its
+      // index).  With the row-tile-fastest grid every wave after the first sees a bound from thousands of columns: few insertions.
       float mx = -INFINITY, sum = 0.f;
       float tv[KC];
       int ti[KC];
 #pragma unroll
       for (int qq = 0; qq < KC; ++qq) { tv[qq] = -INFINITY; ti[qq] = 0x7fffffff; }
+      float thr0 = -INFINITY;
+      if (row_ok && p.row_thr) {
+        uint32_t lo_bits = 0xffffffffu;
+        for (int g = 0; g < p.kc; ++g) lo_bits = min(lo_bits, __ldcg(p.row_thr + (long long)m * KC + g));
+        if (lo_bits != 0u) thr0 = unorder_f32(lo_bits);      // 0 = a slot nobody has written yet: no bound
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int n = n0 + c * 32;
@@ -384,25 +411,28 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 32; ++j) s += expf(v[j] - nmx);   // masked columns: exp(-inf) = 0
         sum = s; mx = nmx;
+        if (cmx >= thr0 && cmx > tv[KC - 1]) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (v[j] > tv[KC - 1]) {                      // strict: an equal value keeps the earlier (lower) index ahead
-            tv[KC - 1] = v[j]; ti[KC - 1] = n + j;
+          for (int j = 0; j < 32; ++j) {
+            if (v[j] > tv[KC - 1] && v[j] >= thr0) {      // strict vs the list: an equal value keeps the earlier (lower) index ahead
+              tv[KC - 1] = v[j]; ti[KC - 1] = n + j;
 #pragma unroll
-            for (int qq = KC - 1; qq > 0; --qq) {
-              if (tv[qq] > tv[qq - 1]) {
-                const float fv = tv[qq]; tv[qq] = tv[qq - 1]; tv[qq - 1] = fv;
-                const int iv = ti[qq]; ti[qq] = ti[qq - 1]; ti[qq - 1] = iv;
+              for (int qq = KC - 1; qq > 0; --qq) {
+                if (tv[qq] > tv[qq - 1]) {
+                  const float fv = tv[qq]; tv[qq] = tv[qq - 1]; tv[qq - 1] = fv;
+                  const int iv = ti[qq]; ti[qq] = ti[qq - 1]; ti[qq - 1] = iv;
+                }
               }
             }
           }
         }
       }
       if (row_ok) {                                     // partials are [M][part], part = 2*tile + half (a half may be empty: -inf / 0)
-        const long long o = (long long)m * (2 * gridDim.x) + 2 * blockIdx.x + half;
+        const long long o = (long long)m * (2 * n_tiles) + 2 * tile_n + half;
         p.o_ms[2 * o] = mx; p.o_ms[2 * o + 1] = sum;
 #pragma unroll
         for (int qq = 0; qq < KC; ++qq) { p.o_val[o * KC + qq] = tv[qq]; p.o_idx[o * KC + qq] = ti[qq]; }
+        if (p.row_thr && mx > thr0) atomicMax(p.row_thr + (long long)m * KC + (2 * tile_n + half) % p.kc, order_f32(mx));
       }
     }
   }
@@ -479,13 +509,14 @@ __global__ void keys_to_tokens_kernel(int M, const unsigned long long* __restric
 
 // ------------------------------------------------------------------ beam bookkeeping
 // One warp per slot: merge the per-tile (max, sum exp, top-KC) partials into log_softmax values of the row's best kc tokens.
+// Each lane keeps the best KC of its share of the candidates (most lists are empty: the epilogue filters against the row's running
+// bound), then kc rounds pick the best lane head (highest value, lowest index on ties) and pop it.
 __global__ void beam_combine_kernel(int S, int n_part, int kc, const float* __restrict__ ms, const float* __restrict__ tv,
                                     const int* __restrict__ ti, float* __restrict__ cand_lp, int* __restrict__ cand_tok) {
-  extern __shared__ float shv[];                       // [n_part*KC] values, then indices
-  const int s = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= S) return;
   const int n = n_part * KC;
-  int* shi = reinterpret_cast<int*>(shv + n);
   float mx = -INFINITY;
   for (int j = lane; j < n_part; j += 32) mx = fmaxf(mx, ms[2 * ((long long)s * n_part + j)]);
 #pragma unroll
@@ -498,27 +529,50 @@ __global__ void beam_combine_kernel(int S, int n_part, int kc, const float* __re
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float logsum = logf(sum);
-  for (int j = lane; j < n; j += 32) { shv[j] = tv[(long long)s * n + j]; shi[j] = ti[(long long)s * n + j]; }
+  // stage the row's candidates in shared memory (independent, coalesced loads), then select from there
+  extern __shared__ float sh_all[];
+  float* shv = sh_all + (size_t)(threadIdx.x >> 5) * 2 * n;
+  int* shi = reinterpret_cast<int*>(shv + n);
+  for (int j = lane; j < n; j += 32) { shi[j] = ti[(long long)s * n + j]; shv[j] = tv[(long long)s * n + j]; }
   __syncwarp();
-  for (int r = 0; r < kc; ++r) {
-    float bv = -INFINITY; int bi = 0x7fffffff, bp = -1;
-    for (int j = lane; j < n; j += 32) {
-      const float v = shv[j]; const int id = shi[j];
-      if (id != 0x7fffffff && (v > bv || (v == bv && id < bi) || bp < 0)) { bv = v; bi = id; bp = j; }
+  float lv[KC];
+  int li[KC];
+#pragma unroll
+  for (int q = 0; q < KC; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
+  for (int j = lane; j < n; j += 32) {
+    const int id = shi[j];
+    if (id == 0x7fffffff) continue;
+    const float v = shv[j];
+    if (v > lv[KC - 1] || (v == lv[KC - 1] && id < li[KC - 1])) {
+      lv[KC - 1] = v; li[KC - 1] = id;
+#pragma unroll
+      for (int q = KC - 1; q > 0; --q) {
+        if (lv[q] > lv[q - 1] || (lv[q] == lv[q - 1] && li[q] < li[q - 1])) {
+          const float fv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = fv;
+          const int iv = li[q]; li[q] = li[q - 1]; li[q - 1] = iv;
+        }
+      }
     }
+  }
+  for (int r = 0; r < kc; ++r) {
+    float bv = lv[0];
+    int bi = li[0], bl = lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (op >= 0 && (bp < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bp = op; }
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bl = ol; }
     }
     if (lane == 0) {
       cand_lp[(long long)s * kc + r] = (bv - mx) - logsum;        // log_softmax as torch computes it: (z - max) - log(sum exp)
-      cand_tok[(long long)s * kc + r] = bp >= 0 ? bi : 0;
+      cand_tok[(long long)s * kc + r] = bi != 0x7fffffff ? bi : 0;
     }
-    if (bp >= 0 && (bp & 31) == lane) shi[bp] = 0x7fffffff;       // taken
-    __syncwarp();
+    if (lane == bl && bi != 0x7fffffff) {                         // pop the winner's head
+#pragma unroll
+      for (int q = 0; q < KC - 1; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
+      lv[KC - 1] = -INFINITY; li[KC - 1] = 0x7fffffff;
+    }
   }
 }
 
@@ -628,10 +682,12 @@ __global__ void beam_hist_kernel(int bw, int D1, BeamMeta old_, BeamMeta new_, c
 __global__ void beam_gather_kernel(int S, int HP, const int* __restrict__ parent,
                                    __half* __restrict__ a1, long long a1_plane, __half* __restrict__ x, long long x_plane,
                                    const __half* __restrict__ h2n, long long h2n_plane,
-                                   float* __restrict__ c1, const float* __restrict__ c1n, float* __restrict__ c2, const float* __restrict__ c2n) {
+                                   float* __restrict__ c1, const float* __restrict__ c1n, float* __restrict__ c2, const float* __restrict__ c2n,
+                                   unsigned int* __restrict__ row_thr) {
   const int s = blockIdx.x, pl = blockIdx.y;
   const long long ps = parent[s];
   if (pl == 0) {
+    if (threadIdx.x < KC) row_thr[(long long)s * KC + threadIdx.x] = 0u;      // the next depth's candidate bounds start from "none"
     for (int u = threadIdx.x; u < HP; u += blockDim.x) {
       a1[(long long)s * HP + u] = x[ps * 2 * HP + u];
       a1[a1_plane + (long long)s * HP + u] = x[x_plane + ps * 2 * HP + u];
@@ -677,9 +733,9 @@ struct Planes {            // an fp16 (hi, lo) operand: rows x k, leading dimens
 static unsigned long long* g_trace_buf = nullptr;     // s2vt_xdec_set_trace: [max][8] stamps, one record per xgemm launch
 static int g_trace_max = 0, g_trace_n = 0;
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MINB = 1>
 static int launch_x(cudaStream_t st, int M, int N, int K, const Planes& A, const Planes& B, XParams p) {
-  constexpr int STAGES = (BN == 128) ? 3 : 4;
+  constexpr int STAGES = (MINB == 2) ? 2 : ((BN == 128) ? 3 : 4);
   constexpr int SMEM = STAGES * (2 * PLANE_A + 2 * BN * BK * 2) + 1024;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_planes(&tmA, A.p, (uint64_t)K, (uint64_t)M, (uint64_t)A.ld, (uint64_t)A.plane, BM);
@@ -693,18 +749,19 @@ static int launch_x(cudaStream_t st, int M, int N, int K, const Planes& A, const
   }
   static bool attr_set = false;
   if (!attr_set) {
-    S2VT_CHECK_CUDA(cudaFuncSetAttribute(xgemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    S2VT_CHECK_CUDA(cudaFuncSetAttribute(xgemm_kernel<BN, EPI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   static int use_pdl = -1;
   if (use_pdl < 0) { const char* e = getenv("S2VT_XDEC_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ceil_div(N, BN), ceil_div(M, BM)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+  cfg.gridDim = p.m_fastest ? dim3(ceil_div(M, BM), ceil_div(N, BN)) : dim3(ceil_div(N, BN), ceil_div(M, BM));
+  cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-  S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xgemm_kernel<BN, EPI>, tmA, tmB, p));
+  S2VT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, xgemm_kernel<BN, EPI, MINB>, tmA, tmB, p));
   S2VT_CHECK_LAUNCH();
   return 0;
 }
@@ -776,10 +833,12 @@ static Weights carve_weights(char* base, const Cfg& g) {
 
 static thread_local cudaStream_t g_side = nullptr;
 static thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local cudaEvent_t g_bev[4] = {nullptr, nullptr, nullptr, nullptr};
 static int side_stream(cudaStream_t* out) {
   if (!g_side) {
     S2VT_CHECK_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) S2VT_CHECK_CUDA(cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) S2VT_CHECK_CUDA(cudaEventCreateWithFlags(&g_bev[i], cudaEventDisableTiming));
   }
   *out = g_side;
   return 0;
@@ -1089,6 +1148,7 @@ struct BeamWs {
   __half *a1, *x, *h2n;
   float *c1, *c1n, *c2, *c2n, *ms, *tv, *cand_lp;
   int *ti, *cand_tok, *nbeam, *done, *was_done, *parent, *n_done;
+  unsigned int* row_thr;
   xd::BeamMeta meta[2];
   size_t bytes;
 };
@@ -1103,13 +1163,15 @@ BeamWs carve_beam(char* base, const Cfg& g, int B, int bw, int D1) {
   w.h2n = (__half*)take(2 * 2 * S * HP);
   w.c1 = (float*)take(4 * S * HP); w.c1n = (float*)take(4 * S * HP);
   w.c2 = (float*)take(4 * S * HP); w.c2n = (float*)take(4 * S * HP);
-  w.ms = (float*)take(4 * 2 * S * 2 * n_part);
-  w.tv = (float*)take(4 * S * 2 * n_part * KC);
-  w.ti = (int*)take(4 * S * 2 * n_part * KC);
+  const size_t n_part2 = 2 * (size_t)ceil_div(g.V, 128);
+  w.ms = (float*)take(4 * 2 * S * n_part2);
+  w.tv = (float*)take(4 * S * n_part2 * KC);
+  w.ti = (int*)take(4 * S * n_part2 * KC);
   w.cand_lp = (float*)take(4 * S * KC);
   w.cand_tok = (int*)take(4 * S * KC);
   w.nbeam = (int*)take(4 * (size_t)B); w.done = (int*)take(4 * (size_t)B); w.was_done = (int*)take(4 * (size_t)B); w.parent = (int*)take(4 * S);
   w.n_done = (int*)take(64);
+  w.row_thr = (unsigned int*)take(4 * S * KC);
   for (int i = 0; i < 2; ++i) {
     w.meta[i].key = (float*)take(4 * S); w.meta[i].tok = (int*)take(4 * S); w.meta[i].len = (int*)take(4 * S);
     w.meta[i].fin = (int*)take(4 * S); w.meta[i].hist = (int*)take(4 * S * D1);
@@ -1156,12 +1218,19 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
   beam_init_kernel<<<ceil_div(B, 128), 128, 0, st>>>(B, beam_width, D1, g.sos, w.meta[0], w.nbeam, w.done, out_tokens, out_len);
   S2VT_CHECK_LAUNCH();
   S2VT_CHECK_CUDA(cudaMemsetAsync(w.n_done, 0, sizeof(int), st));
+  S2VT_CHECK_CUDA(cudaMemsetAsync(w.row_thr, 0, 4 * (size_t)S * KC, st));
   beam_state_init_kernel<<<S, 128, 0, st>>>(B, beam_width, HP, e.o1p + (long long)L * BH, (long long)(L + 1) * BH, e.c1 + (long long)((L - 1) & 1) * BH,
                                             e.h2p + (long long)(L & 1) * BH, 2 * BH, e.c2 + (long long)((L - 1) & 1) * BH,
                                             w.a1, SH, w.x, 2 * SH, w.c1, w.c2);
   S2VT_CHECK_LAUNCH();
   const Planes WH1{W.hh1, HP, (long long)G * HP, W.inv + INV_HH1}, WC2{W.cat2, 2 * HP, (long long)G * 2 * HP, W.inv + INV_CAT2};
   const Planes WO{W.out, HP, (long long)g.V * HP, W.inv + INV_OUT};
+  const int n_part2 = 2 * ceil_div(g.V, 128);                 // candidate lists per row: one per tile and epilogue warp group
+  const size_t combine_smem = (size_t)2 * n_part2 * KC * 8;
+  S2VT_REQUIRE(combine_smem <= 200 * 1024, "s2vt_xdec_beam: vocabulary too large for the candidate merge (V <= 102400)");
+  if (combine_smem > 48 * 1024)
+    S2VT_CHECK_CUDA(cudaFuncSetAttribute(beam_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int chunk = 0;
   for (int depth = 0; depth < max_depth; ++depth) {
     const xd::BeamMeta& mo = w.meta[depth & 1];
     const xd::BeamMeta& mn = w.meta[(depth + 1) & 1];
@@ -1181,22 +1250,32 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
     {   // out_linear + log_softmax + top-k partials (S2VTModel.py:213-216)
       XParams p{};
       p.bias = W.bout; p.o_ms = w.ms; p.o_val = w.tv; p.o_idx = w.ti;
+      p.row_thr = w.row_thr; p.kc = kc; p.m_fastest = 1;
       Planes A{w.h2n, HP, SH, W.inv + INV_H};
       X_TRY((launch_x<128, EPI_BEAM>(st, S, g.V, HP, A, WO, p)));
     }
-    beam_combine_kernel<<<S, 32, (size_t)2 * n_part * KC * 8, st>>>(S, 2 * n_part, kc, w.ms, w.tv, w.ti, w.cand_lp, w.cand_tok);
+    beam_combine_kernel<<<ceil_div(S, 2), 64, combine_smem, st>>>(S, n_part2, kc, w.ms, w.tv, w.ti, w.cand_lp, w.cand_tok);
     S2VT_CHECK_LAUNCH();
     beam_select_kernel<<<ceil_div(B, 32), 32, 0, st>>>(B, beam_width, topk, kc, D1, g.eos, len_pen, mo, mn, w.cand_lp, w.cand_tok,
                                                       w.nbeam, w.done, w.was_done, w.parent, out_len, w.n_done);
     S2VT_CHECK_LAUNCH();
     beam_hist_kernel<<<S, 32, 0, st>>>(beam_width, D1, mo, mn, w.parent, w.was_done, out_tokens);
     S2VT_CHECK_LAUNCH();
-    beam_gather_kernel<<<dim3(S, 4), 128, 0, st>>>(S, HP, w.parent, w.a1, SH, w.x, 2 * SH, w.h2n, SH, w.c1, w.c1n, w.c2, w.c2n);
+    beam_gather_kernel<<<dim3(S, 4), 128, 0, st>>>(S, HP, w.parent, w.a1, SH, w.x, 2 * SH, w.h2n, SH, w.c1, w.c1n, w.c2, w.c2n, w.row_thr);
     S2VT_CHECK_LAUNCH();
     if (check_every > 0 && (depth + 1) % check_every == 0 && depth + 1 < max_depth) {
-      S2VT_CHECK_CUDA(cudaMemcpyAsync(host_flag, w.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
-      S2VT_CHECK_CUDA(cudaStreamSynchronize(st));
-      if (*host_flag >= B) break;
+      // Early exit without draining the stream: the count of finished videos after this chunk of depths goes to a pinned slot, and the
+      // host waits for the PREVIOUS chunk's count before it enqueues the next one -- one chunk is always queued behind the running
+      // one.  Depths run past the point where every video has finished change nothing (finished videos are frozen).
+      const int slot = chunk & 3;
+      S2VT_CHECK_CUDA(cudaMemcpyAsync(host_flag + slot, w.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      S2VT_CHECK_CUDA(cudaEventRecord(g_bev[slot], st));
+      if (chunk >= 1) {
+        const int prev = (chunk - 1) & 3;
+        S2VT_CHECK_CUDA(cudaEventSynchronize(g_bev[prev]));
+        if (host_flag[prev] >= B) break;
+      }
+      ++chunk;
     }
   }
   return 0;

@@ -419,7 +419,7 @@ class S2VT(nn.Module):
         self._adam_shadow = None                # set by FusedAdam.attach(): its kernel keeps bf16 copies of the weights current
         self._shadow = EB.ShadowCache()         # bf16 mirrors of the weights (derived, rebuilt lazily, never saved)
         self._xdec = None                       # (key, cfg, weight planes, workspace) of the tensor-core decode path
-        self.beam_check_every = 6               # beam search: host looks for "every video finished" this often (0 = never)
+        self.beam_check_every = 3               # beam search: the host looks for "every video finished" every this many depths (0 = never)
 
     def __getstate__(self):
         st = self.__dict__.copy()               # whole-module pickles (train.py:167) carry parameters only
@@ -429,7 +429,7 @@ class S2VT(nn.Module):
 
     def __setstate__(self, st):
         st.setdefault("_xdec", None)
-        st.setdefault("beam_check_every", 6)
+        st.setdefault("beam_check_every", 3)
         self.__dict__.update(st)
 
     # ---- tensor-core decode path ("x": fp32 operands as fp16 hi/lo planes, csrc/xdec_sm100.cu)
@@ -592,7 +592,7 @@ class S2VT(nn.Module):
                 pen = torch.tensor([0.0] + [pow(float(n), 0.7) for n in range(1, max_beam_depth + 3)], dtype=torch.float32).to(dev)
                 X["pen"][max_beam_depth] = pen
             if X["flag"] is None:
-                X["flag"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+                X["flag"] = torch.zeros(4, dtype=torch.int32).pin_memory()
             toks = torch.empty(B, max_beam_depth + 1, dtype=torch.int64, device=dev)
             lens = torch.empty(B, dtype=torch.int32, device=dev)
             X["ws"] = ops.xdec_beam(X["cfg"], X["wbuf"], feats, int(beam_width), int(max_beam_depth), self.beam_topk, pen, toks, lens,

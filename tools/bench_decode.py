@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--decode", default="x", choices=["x", "fp32"], help="x: tcgen05 fp16-split path, fp32: CUDA-core FFMA path")
-    ap.add_argument("--beam-batch", type=int, default=256)
+    ap.add_argument("--beam-batch", type=int, default=230)
     ap.add_argument("--cpu-videos", type=int, default=0, help="also time the CPU port's greedy decode on this many videos")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
