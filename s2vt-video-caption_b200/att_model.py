@@ -307,11 +307,12 @@ def att_backward_bf16(P, S, saved, targets, dl_bf, need_dfeats: bool):
     G = {}
     new = lambda *s: torch.empty(*s, device=dev)                                    # noqa: E731
     G["out_linear.weight"] = new(V, H)
-    EB.gemm(V, H, R, dl_bf, V, True, out_d, H, True, G["out_linear.weight"], dense(H))
+    ldv = dl_bf.stride(0)                                                            # pad8(V): EB.dlogits_buffer
+    EB.gemm(V, H, R, dl_bf, ldv, True, out_d, H, True, G["out_linear.weight"], dense(H))
     G["out_linear.bias"] = new(V)
-    EB.colsum_bf16(dl_bf, R, V, V, G["out_linear.bias"])
+    EB.colsum_bf16(dl_bf, R, V, ldv, G["out_linear.bias"])
     dout_d = new(R, H)
-    EB.gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout_d, dense(H))
+    EB.gemm(R, H, V, dl_bf, ldv, False, S["out_linear.weight"], H, True, dout_d, dense(H))
     dg_d = torch.empty(R, 4 * H, dtype=BF, device=dev)
     EB.lstm_bwd(Lq - 1, B, H, 0, dout_d, saved["g_d"], saved["c_d"], S["decoder.weight_hh_l0.T"], dg_d)
     Wd = S["decoder.weight_ih_l0"]
@@ -383,7 +384,8 @@ class _AttTrainBf16Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dl):
         B, Lm1, V = dl.shape
-        dl_tm = dl.transpose(0, 1).contiguous().view(Lm1 * B, V).to(torch.bfloat16)    # layout glue for the caller-supplied gradient
+        dl_tm = EB.dlogits_buffer(Lm1 * B, V, dl.device)                                # layout glue for the caller-supplied gradient
+        dl_tm.view(Lm1, B, V).copy_(dl.transpose(0, 1))
         G, dfeats = att_backward_bf16(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1])
         ctx.saved = None
         return (None, dfeats, None) + tuple(G[k] for k in ATT_PARAM_ORDER)

@@ -38,10 +38,11 @@ class _MeanCEFn(torch.autograd.Function):
         if prod is not None:
             from . import engine_bf16 as EB
             B, Lm1 = prod.targets.shape
-            dl = torch.empty(R, V, dtype=torch.bfloat16, device=logits2d.device)
+            dl = EB.dlogits_buffer(R, V, logits2d.device)
+            ldv = dl.stride(0)
             # logits row r = b*(L-1) + t  ->  gradient row t*B + b
             EB.ce_bf16(logits2d, R, V, target1d, 0, dense(1), dlogits=dl, gscale=g.contiguous().to(torch.float32), row_lse=ctx.lse,
-                       have_lse=True, omap=rowmap(Lm1, V, B * V))
+                       have_lse=True, omap=rowmap(Lm1, ldv, B * ldv))
             prod.dl_bf16 = dl if prod.dl_bf16 is None else prod.dl_bf16 + dl
             return torch.zeros((), device=logits2d.device).expand(R, V), None      # zero-stride placeholder (see the producer's backward)
         dl = torch.empty_like(logits2d)

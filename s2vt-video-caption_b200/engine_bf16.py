@@ -27,8 +27,14 @@ BULK_ELT_CTAS = int(_os.environ.get("S2VT_BULK_ELT_CTAS", "104"))
 
 
 def supported(H: int, E: int, F: int, V: int) -> bool:
-    """Shapes the tensor-core path covers: cluster recurrence needs H % 128 == 0 and H <= 512; TMA needs 16-byte rows."""
-    return H % 128 == 0 and 128 <= H <= 512 and E % 8 == 0 and F % 8 == 0 and V % 8 == 0
+    """Shapes the tensor-core path covers: cluster recurrence needs H % 128 == 0 and H <= 512; TMA needs 16-byte rows, i.e. E and F
+    multiples of 8 (they are leading dimensions of weights in the checkpoint layout).  The vocabulary size is free: V is a leading
+    dimension only of the bf16 logits / dlogits, which are this engine's own buffers and get a row pitch of pad8(V)."""
+    return H % 128 == 0 and 128 <= H <= 512 and E % 8 == 0 and F % 8 == 0 and V >= 1
+
+
+def pad8(n: int) -> int:
+    return (int(n) + 7) // 8 * 8
 
 
 # ------------------------------------------------------------------------------------------------ thin wrappers
@@ -206,24 +212,30 @@ def _chain_stream(dev) -> torch.cuda.Stream:
 
 # ------------------------------------------------------------------------------------------------ forward / backward
 def vocab_ce_fwd(R, V, K, A, a_off, W, bias, targets_full, t_off, tmap, loss):
-    """out_linear fused with the loss statistics: returns (bf16 logits [R,V], row log-sum-exp [R]); `loss` receives the mean CE."""
+    """out_linear fused with the loss statistics: returns (bf16 logits [R,V] with row pitch pad8(V), row log-sum-exp [R]); `loss`
+    receives the mean CE."""
     lib = L.load()
     dev = A.device
-    logits = torch.empty(R, V, dtype=BF, device=dev)
+    logits = torch.empty(R, pad8(V), dtype=BF, device=dev)[:, :V]
     part = torch.empty(int(lib.s2vt_vocab_ce_ws_bytes(R, V)), dtype=torch.uint8, device=dev)
     ztgt = torch.empty(R, device=dev)
     lse = torch.empty(R, device=dev)
     row_loss = torch.empty(R, device=dev)
     with ops._timed("gemm_bf16_persist[%dx%dx%d NN bf16out +CE]" % (R, V, K), 2.0 * R * V * K, 2.0 * (R * K + V * K) + 2.0 * R * V):
-        rc = lib.s2vt_vocab_ce_fwd_bf16(L.stream_ptr(dev), R, V, K, L.ptr(A, a_off), K, L.ptr(W), K, L.ptr(bias), L.ptr(logits), V,
+        rc = lib.s2vt_vocab_ce_fwd_bf16(L.stream_ptr(dev), R, V, K, L.ptr(A, a_off), K, L.ptr(W), K, L.ptr(bias), L.ptr(logits), logits.stride(0),
                                         L.ptr(targets_full, t_off), tmap, L.ptr(part), L.ptr(ztgt), L.ptr(lse), L.ptr(row_loss), L.ptr(loss))
     L.check(rc, "s2vt_vocab_ce_fwd_bf16")
     return logits, lse
 
 
+def dlogits_buffer(R: int, V: int, dev) -> torch.Tensor:
+    """bf16 [R, V] view with row pitch pad8(V): what train_backward takes as dL/dlogits (TMA rows must be 16-byte aligned)."""
+    return torch.empty(R, pad8(V), dtype=BF, device=dev)[:, :V]
+
+
 def ce_dlogits_inplace(logits_bf, R, V, lse, targets_full, t_off, tmap, gscale):
     with ops._timed("ce_bf16", 0.0, 4.0 * R * V):
-        rc = L.load().s2vt_ce_dlogits_inplace_bf16(L.stream_ptr(logits_bf.device), L.ptr(logits_bf), R, V, V, L.ptr(lse), L.ptr(targets_full, t_off),
+        rc = L.load().s2vt_ce_dlogits_inplace_bf16(L.stream_ptr(logits_bf.device), L.ptr(logits_bf), R, V, logits_bf.stride(0), L.ptr(lse), L.ptr(targets_full, t_off),
                                                    tmap, L.ptr(gscale))
     L.check(rc, "s2vt_ce_dlogits_inplace_bf16")
     return logits_bf
@@ -395,7 +407,7 @@ def _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, events):
         ctr = _wave_counters(dev)
         ctr[2:4].zero_()
         ctr[5].zero_()
-        gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=Lq * B * H)
+        gemm(R, H, V, dl_bf, dl_bf.stride(0), False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=Lq * B * H)
         ev_dout2.record(chain)
         lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2, tiles_per_cluster=ntl_lead,
                  sync=(bounds, ctr[2], None, 0))
@@ -493,9 +505,12 @@ def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, c
 
 def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool, gout: Optional[Dict[str, torch.Tensor]] = None,
                    on_ready=None):
-    """BPTT for train_forward: dl_bf = dL/dlogits as bf16 [(L-1)B, V] in time-major row order.
-    Returns fp32 grads keyed by parameter name (+ 'feats' when requested)."""
+    """BPTT for train_forward: dl_bf = dL/dlogits as bf16 [(L-1)B, V] in time-major row order, row pitch a multiple of 8 elements
+    (pad8(V): allocate with dlogits_buffer()).  Returns fp32 grads keyed by parameter name (+ 'feats' when requested)."""
     B, Lq, F, H, E, V, T = saved["dims"]
+    ldv = dl_bf.stride(0)
+    if ldv % 8 or dl_bf.stride(1) != 1:
+        raise ValueError("dl_bf must have unit column stride and a row pitch that is a multiple of 8 (engine_bf16.dlogits_buffer)")
     dev = dl_bf.device
     R = (Lq - 1) * B
     out1, out2, xproj = saved["out1"], saved["out2"], saved["xproj"]
@@ -528,7 +543,7 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
         ev_dout2 = _wavefront_backward(S, saved, dl_bf, chain, dout2, dg2, dout1, dg1, (ev_dout2, ev_dg2, ev_dout1, ev_dg1))
     else:
         with torch.cuda.stream(chain):
-            gemm(R, H, V, dl_bf, V, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
+            gemm(R, H, V, dl_bf, ldv, False, S["out_linear.weight"], H, True, dout2, dense(H), c_off=hdec)
             ev_dout2.record(chain)
             lstm_bwd(T, B, H, Lq, dout2, saved["g2"], saved["c2"], S["word_rnn.weight_hh_l0.T"], dg2)
             ev_dg2.record(chain)
@@ -547,7 +562,7 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     gW = _new("out_linear.weight", V, H)
     gb = _new("out_linear.bias", V)
     with beside_sweeps(capped):
-        gemm(V, H, R, dl_bf, V, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True, bulk=capped)
+        gemm(V, H, R, dl_bf, ldv, True, out2, H, True, gW, dense(H), b_off=hdec, short_ctas=True, bulk=capped)
         G["out_linear.weight"] = gW
         _ready("out_linear")                        # (the bias gradient belongs to the embedding bucket, dp.BUCKETS)
     # ---- word_rnn weight / bias / embedding gradients (beside the vid_rnn sweep)
@@ -559,7 +574,7 @@ def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool,
     with torch.cuda.stream(sB):
         sB.wait_event(ev_bulk)
         with beside_sweeps(capped):
-            colsum_bf16(dl_bf, R, V, V, gb)
+            colsum_bf16(dl_bf, R, V, ldv, gb)
         G["out_linear.bias"] = gb
         sB.wait_event(ev_dg2)
         with beside_sweeps(capped):

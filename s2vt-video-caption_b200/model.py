@@ -376,9 +376,10 @@ class _TrainLogitsBf16Fn(torch.autograd.Function):
             dl_tm = fused                       # `dl` is MaskCriterion's zero-stride placeholder: nothing else contributed
         else:
             # a caller-supplied gradient: [B, L-1, V] f32 -> time-major [(L-1)B, V] bf16
-            dl_tm = dl.transpose(0, 1).contiguous().view(Lm1 * B, V).to(torch.bfloat16)
+            dl_tm = EB.dlogits_buffer(Lm1 * B, V, dl.device)
+            dl_tm.view(Lm1, B, V).copy_(dl.transpose(0, 1))
             if fused is not None:
-                dl_tm = dl_tm + fused
+                dl_tm += fused
         direct, cb = _direct_grad_targets(ctx.module)
         G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
         ctx.saved = None
@@ -455,8 +456,8 @@ class S2VT(nn.Module):
         ok = EB.supported(self.dim_hid, self.dim_embed, self.feat_dim, self.vocab_size)
         if self.train_precision == "bf16":
             if not ok:
-                raise NotImplementedError("train_precision='bf16' needs dim_hid % 128 == 0, dim_hid <= 512 and dim_embed, feat_dim, "
-                                          "vocab_size multiples of 8; use train_precision='fp32' for other shapes")
+                raise NotImplementedError("train_precision='bf16' needs dim_hid % 128 == 0, dim_hid <= 512 and dim_embed, feat_dim "
+                                          "multiples of 8 (any vocab_size); use train_precision='fp32' for other shapes")
             return True
         if self.train_precision == "fp32":
             return False
