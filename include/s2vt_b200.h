@@ -332,6 +332,19 @@ int s2vt_vocab_ce_fwd_bf16(void* stream, int R, int V, int K, const void* A_bf16
 int s2vt_ce_dlogits_inplace_bf16(void* stream, void* logits_bf16, int64_t R, int V, int64_t ld, const float* row_lse,
                                  const int64_t* targets, s2vt_rowmap tmap, const float* gscale);
 
+/* ------------------------------------------------------------------ LSTM recurrence / BPTT for any hidden size (H % 8 == 0)
+ * One tcgen05 GEMM per time step (bf16 operands, fp32 accumulation) whose epilogue is the LSTM cell (forward) or the gate-gradient
+ * arithmetic (backward); used where the persistent cluster kernels do not apply (H > 512 or H % 128 != 0, e.g. the paper sizing
+ * H = 1000).  Time-major layouts, row = t*B + b:
+ *   pre [n_pre,B,4H] f32 and gates [T,B,4H] bf16 have their columns INTERLEAVED (4u+g); w_hh_il = W_hh with rows interleaved alike;
+ *   dgates [T,B,4H] bf16 comes out in natural gate order (g*H+u), the layout of the time-batched weight-gradient products;
+ *   w_hh_t = W_hh^T [H,4H] bf16;  cells [T,B,H] f32;  out [T,B,H] bf16;  dc_ws [B,H] f32 scratch.
+ * replaces: nn.LSTM (S2VTModel.py:19-22,67,77) and its autograd (train.py:124). */
+int s2vt_lstm_steps_fwd_bf16(void* stream, int T, int B, int H, int n_pre, const float* pre, const float* bias_il,
+                             const void* w_hh_il, void* out, void* gates, float* cells);
+int s2vt_lstm_steps_bwd_bf16(void* stream, int T, int B, int H, int dout_t0, const float* dout, const void* gates,
+                             const float* cells, const void* w_hh_t, void* dgates, float* dc_ws);
+
 /* ------------------------------------------------------------------ exact-grade decode on the tensor cores ("x" path)
  * fp32 operands are scaled by a power of two and split into two fp16 planes (hi, lo); a product is three
  * tcgen05.mma.kind::f16 passes (hi*lo + lo*hi + hi*hi) into one fp32 TMEM accumulator: per-term error <= 2^-21, below what an

@@ -302,6 +302,8 @@ int lstm_bf16_error_clear();
 int lstm_bwd_bf16_error_clear();
 int gemm_persist_error_clear();
 int xdec_error_clear();
+int lstm_step_error_flag();
+int lstm_step_error_clear();
 int launch_gemm_persist(cudaStream_t st, int M, int N, int K, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn,
                         void* C, int64_t ldc, int out_bf16, const float* bias, int accumulate);
 void gemm_persist_set_max_ctas(int n);
@@ -321,12 +323,12 @@ extern "C" int s2vt_gemm_bf16_set_mode(int max_ctas, int use_persistent) {
 extern "C" int s2vt_device_error_flag(void* stream) {
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -2;
   const int a = read_sm100_error_flag(), b = lstm_bf16_error_flag(), c = lstm_bwd_bf16_error_flag(), d = gemm_persist_error_flag();
-  const int x = xdec_error_flag();
-  return a != 0 ? a : (b != 0 ? b : (c != 0 ? c : (d != 0 ? d : x)));
+  const int x = xdec_error_flag(), y = lstm_step_error_flag();
+  return a != 0 ? a : (b != 0 ? b : (c != 0 ? c : (d != 0 ? d : (x != 0 ? x : y))));
 }
 
 extern "C" int s2vt_device_error_clear(void) {
-  return clear_sm100_error_flag() | lstm_bf16_error_clear() | lstm_bwd_bf16_error_clear() | gemm_persist_error_clear() | xdec_error_clear();
+  return clear_sm100_error_flag() | lstm_bf16_error_clear() | lstm_bwd_bf16_error_clear() | gemm_persist_error_clear() | xdec_error_clear() | lstm_step_error_clear();
 }
 
 extern "C" int s2vt_gemm_bf16(void* stream, int M, int N, int K,

@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from . import engine_bf16 as EB
+from . import engine_step as ES
 from . import ops
 from .lib import dense, rowmap, require_cuda
 
@@ -304,10 +305,10 @@ class _TrainLossFn(torch.autograd.Function):
         loss = torch.empty((), device=feats.device)
         # row (t,b) of the time-major logits is scored against targets_full[b, t+1]
         if ctx.bf16:
-            ctx.S = module._shadow.get(P, getattr(module, '_adam_shadow', None))
+            ctx.eng, ctx.S = module._engine_and_shadows(P)
             # vocab projection + loss statistics in one kernel: the logits are written once, as bf16
-            logits, saved = EB.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False,
-                                             ce=dict(targets_full=targets_full, t_off=1, tmap=rowmap(B, 1, L), loss=loss))
+            logits, saved = ctx.eng.train_forward(P, ctx.S, feats, tin, stash=need, batch_major_logits=False,
+                                                  ce=dict(targets_full=targets_full, t_off=1, tmap=rowmap(B, 1, L), loss=loss))
         else:
             logits, saved = train_forward_f32(P, feats, tin, stash=need, batch_major_logits=False)
             ops.ce_f32(logits, (L - 1) * B, V, targets_full, 1, rowmap(B, 1, L), loss)
@@ -323,7 +324,7 @@ class _TrainLossFn(torch.autograd.Function):
         direct, cb = _direct_grad_targets(ctx.module)
         if ctx.bf16:
             dl = EB.ce_dlogits_inplace(logits, (L - 1) * B, V, ctx.saved["lse"], ctx.tfull, 1, rowmap(B, 1, L), g)
-            G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
+            G = ctx.eng.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
             grads, dfeats = [G[k] for k in PARAM_ORDER], G.get("feats")
         else:
             scratch = torch.empty((), device=logits.device)
@@ -356,8 +357,8 @@ class _TrainLogitsBf16Fn(torch.autograd.Function):
     def forward(ctx, module, feats, targets, *params):
         P = dict(zip(PARAM_ORDER, params))
         need = any(ctx.needs_input_grad)
-        ctx.S = module._shadow.get(P, getattr(module, '_adam_shadow', None))
-        logits, saved = EB.train_forward(P, ctx.S, feats, targets, stash=need, batch_major_logits=True)
+        ctx.eng, ctx.S = module._engine_and_shadows(P)
+        logits, saved = ctx.eng.train_forward(P, ctx.S, feats, targets, stash=need, batch_major_logits=True)
         ctx.saved, ctx.P, ctx.targets, ctx.module = saved, P, targets, module
         ctx.dl_bf16, ctx.logits_numel = None, logits.numel()
         if need:
@@ -381,7 +382,7 @@ class _TrainLogitsBf16Fn(torch.autograd.Function):
             if fused is not None:
                 dl_tm += fused
         direct, cb = _direct_grad_targets(ctx.module)
-        G = EB.train_backward(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
+        G = ctx.eng.train_backward(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
         ctx.saved = None
         return (None, G.get("feats"), None) + _finish_grads(ctx.module, direct, [G[k] for k in PARAM_ORDER])
 
@@ -420,17 +421,20 @@ class S2VT(nn.Module):
         self._adam_shadow = None                # set by FusedAdam.attach(): its kernel keeps bf16 copies of the weights current
         self._shadow = EB.ShadowCache()         # bf16 mirrors of the weights (derived, rebuilt lazily, never saved)
         self._xdec = None                       # (key, cfg, weight planes, workspace) of the tensor-core decode path
+        self._shadow_step = None                # engine_step.ShadowCache (shapes outside the cluster kernels' range)
         self.beam_check_every = 3               # beam search: the host looks for "every video finished" every this many depths (0 = never)
 
     def __getstate__(self):
         st = self.__dict__.copy()               # whole-module pickles (train.py:167) carry parameters only
         st["_grad_views"], st["_on_bucket_ready"], st["_adam_shadow"], st["_shadow"] = None, None, None, EB.ShadowCache()
         st["_xdec"] = None
+        st["_shadow_step"] = None
         return st
 
     def __setstate__(self, st):
         st.setdefault("_xdec", None)
         st.setdefault("beam_check_every", 3)
+        st.setdefault("_shadow_step", None)
         self.__dict__.update(st)
 
     # ---- tensor-core decode path ("x": fp32 operands as fp16 hi/lo planes, csrc/xdec_sm100.cu)
@@ -450,14 +454,33 @@ class S2VT(nn.Module):
             self._xdec = dict(key=key, cfg=cfg, wbuf=wbuf, ws=None, flag=None, pen={})
         return self._xdec
 
+    def _bf16_engine(self):
+        """The tensor-core training engine for this shape: engine_bf16 (persistent cluster recurrences: H % 128 == 0, H <= 512, E and F
+        multiples of 8), else engine_step (one launch per time step: any H % 8 == 0, F % 8 == 0, e.g. H = 500 / 1000), else None."""
+        dims = (self.dim_hid, self.dim_embed, self.feat_dim, self.vocab_size)
+        if EB.supported(*dims):
+            return EB
+        # ('auto' leaves toy shapes, H < 128, on the exact path; train_precision='bf16' takes any shape the step engine supports)
+        if ES.supported(*dims) and (self.train_precision == "bf16" or self.dim_hid >= 128):
+            return ES
+        return None
+
+    def _engine_and_shadows(self, P):
+        eng = self._bf16_engine()
+        if eng is EB:
+            return EB, self._shadow.get(P, getattr(self, '_adam_shadow', None))
+        if getattr(self, "_shadow_step", None) is None:
+            self._shadow_step = ES.ShadowCache()
+        return ES, self._shadow_step.get(P)
+
     def _use_bf16(self) -> bool:
         """train_precision: 'bf16' = tensor cores (raises if the shapes are unsupported), 'fp32' = exact CUDA-core path,
         'auto' = bf16 whenever the shapes allow it."""
-        ok = EB.supported(self.dim_hid, self.dim_embed, self.feat_dim, self.vocab_size)
+        ok = self._bf16_engine() is not None
         if self.train_precision == "bf16":
             if not ok:
-                raise NotImplementedError("train_precision='bf16' needs dim_hid % 128 == 0, dim_hid <= 512 and dim_embed, feat_dim "
-                                          "multiples of 8 (any vocab_size); use train_precision='fp32' for other shapes")
+                raise NotImplementedError("train_precision='bf16' needs dim_hid and feat_dim to be multiples of 8 (any dim_embed, any "
+                                          "vocab_size); use train_precision='fp32' for other shapes")
             return True
         if self.train_precision == "fp32":
             return False

@@ -651,3 +651,79 @@ def test_vocab_not_a_multiple_of_8_stays_on_tensor_cores(dev, V):
             rel = (p.grad - ref[k]).norm().item() / max(1e-30, ref[k].norm().item())
             assert rel <= 3e-2, (route, k, rel)
     assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+
+
+# ------------------------------------------------------------------ shapes outside the cluster kernels' range (engine_step)
+@pytest.mark.parametrize("dims", [(210, 64, 72, 20, 6, 9), (300, 48, 200, 100, 7, 130)])
+def test_step_engine_matches_exact_path(dev, dims):
+    """H not a multiple of 128 (and E, V not multiples of 8): the per-step tensor-core recurrence + BPTT against the exact fp32 path of
+    the same module, fused and API routes; then five optimizer steps through DataParallelTrainer with graph replay."""
+    from s2vt_b200 import engine_step as ES
+    from s2vt_b200.dp import DataParallelTrainer
+    V, F, H, E, Lq, B = dims
+    torch.manual_seed(12)
+    mb = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    mf = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="fp32").to(dev)
+    mf.load_state_dict(mb.state_dict())
+    assert mb._bf16_engine() is ES
+    g = torch.Generator().manual_seed(4)
+    feats = torch.randn(B, Lq, F, generator=g).to(dev)
+    targets = torch.randint(0, V, (B, Lq), generator=g).to(dev)
+    mask = torch.ones(B, Lq, device=dev)
+    ff = feats.clone().requires_grad_(True)
+    lf = mf.forward_loss(ff, targets)
+    lf.backward()
+    ref = {k: p.grad.clone() for k, p in mf.named_parameters()}
+    ref["feats"] = ff.grad.clone()
+    for route in ("fused", "api"):
+        for p in mb.parameters():
+            p.grad = None
+        fb = feats.clone().requires_grad_(True)
+        if route == "fused":
+            lb = mb.forward_loss(fb, targets)
+        else:
+            lb = s2vt_b200.MaskCriterion()(mb(fb, targets=targets[:, :-1], mode="train"), targets, mask)
+        lb.backward()
+        assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+        assert abs(lb.item() - lf.item()) <= 2e-3 * abs(lf.item()), (route, lb.item(), lf.item())
+        got = {k: p.grad for k, p in mb.named_parameters()}
+        got["feats"] = fb.grad
+        for k, gv in got.items():
+            rel = (gv - ref[k]).norm().item() / max(1e-30, ref[k].norm().item())
+            print("step engine %-5s %-24s rel-L2 %.3e" % (route, k, rel))
+            assert rel <= 3e-2, (route, k, rel)
+    del lb, lf
+    for p in mb.parameters():
+        p.grad = None
+    opt = s2vt_b200.FusedAdam(mb.parameters(), lr=1e-3)
+    tr = DataParallelTrainer(mb, opt, cuda_graph=True)
+    losses = [float(tr.step(feats, targets).item()) for _ in range(6)]
+    assert tr.replays >= 3 and losses[-1] < losses[0], (tr.replays, losses)
+    tr.check_device_errors()
+
+
+def test_step_engine_paper_sizing_vs_reference_golden(dev):
+    """BASELINE configs[3] sizing (H = 1000, E = 500, F = 2048): loss and sampled gradients of the unmodified reference (paper.npz)."""
+    from s2vt_b200 import engine_step as ES
+    g, model, tf, tt, tm, c = _bf16_model("paper", dev)
+    assert model._bf16_engine() is ES
+    tf = tf.requires_grad_(True)
+    logits = model(tf, targets=tt[:, :-1], mode="train")
+    loss = s2vt_b200.MaskCriterion()(logits, tt, tm)
+    loss.backward()
+    assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+    ls = logits.detach().cpu().numpy().reshape(-1)[::997]
+    ref = g["logits_sample"]
+    print("\n" + _report("logits (paper sizing)", ls, ref), " sigma_ref %.3e" % ref.std())
+    assert abs(loss.item() - float(g["loss"])) <= 1e-3 * float(g["loss"])
+    assert np.abs(ls - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max()) + 2e-2 * ref.std()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
+    grads["feats"] = tf.grad.cpu().numpy()
+    for k, gv in grads.items():
+        if "grad_full/" + k in g:
+            rs, gs = g["grad_full/" + k].reshape(-1), gv.reshape(-1)
+        else:
+            rs, gs = g["grad_sample/" + k], gv.reshape(-1)[::997]
+        rel = np.linalg.norm(gs.astype(np.float64) - rs) / max(1e-30, np.linalg.norm(rs.astype(np.float64)))
+        print("grad %-24s rel-L2 err (sampled) %.3e" % (k, rel))
+        assert rel <= 2e-2, k
