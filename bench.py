@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("S2VT_BENCH_PRECISION", "auto"))
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-resident timed loop and the end-to-end loop")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -464,7 +465,7 @@ def main():
     final_loss = float(loss.item())
 
     # ---- the same loop over >= 2000 steps: seconds of continuous load, clocks at their sustained value
-    n_sus = max(2000, args.steps)
+    n_sus = max(2000, args.steps) if not args.quick else args.steps
     sync_all()
     t_sus0 = time.time()
     e0.record()
@@ -555,7 +556,7 @@ def main():
     for i in range(3):
         api_step(i)
     sync_all()
-    n_api = min(args.steps, 20)
+    n_api = min(args.steps, 20) if not args.quick else 2
     e0.record()
     for i in range(n_api):
         api_step(i)
@@ -570,7 +571,7 @@ def main():
                         "[B,79,V] materialised as the API promises" + ("; no gradient all-reduce on this path (single-process loop body)" if world > 1 else "")}
 
     # ---- decode: greedy / beam captions per second on this rank's videos
-    decode = decode_run(s2vt_b200, dev, rank, world, sync_all, peaks)
+    decode = decode_run(s2vt_b200, dev, rank, world, sync_all, peaks) if not args.quick else None
 
     # ---- per-kernel-family timing of one extra instrumented step (CUDA events on the launching stream)
     with ops.profile() as prof:
@@ -639,7 +640,7 @@ def main():
         "roofline": roofline, "roofline_all": roofline_all, "kernels": kernels, "gemm_detail": gemm_detail,
         "step_tflops": round(world * B * FLOP_PER_VIDEO_TRAIN / (ms_step * 1e-3) / 1e12, 3), "loss": final_loss,
     }
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    if world == 1 and rank == 0 and not args.no_cpu_baseline and not args.quick:
         line["gpu_incumbent"] = gpu_incumbent_run(dev, B)
         r = cpu_reference_run(4, 1, 8, decode=True)
         line["cpu_baseline"] = {"value": round(r["value"], 2), "unit": "videos/s", "cores": r["cores"], "kind": r["kind"],

@@ -254,9 +254,16 @@ def att_bf16_supported(H, E, F, V):
     return EB.supported(H, E, F, V)
 
 
-def att_forward_bf16(P, S, feats, targets, stash: bool):
+def _side_by_side(B: int) -> bool:
+    """The two encoder directions are independent: run them on two streams.  At most 7 clusters of 16 CTAs fit on the part, so the
+    second direction takes two batch tiles per cluster (half the SMs at ~1.25x the step time) and both sweeps are resident at once."""
+    return EB.WAVEFRONT and (B + 15) // 16 + (B + 31) // 32 <= 7
+
+
+def att_forward_bf16(P, S, feats, targets, stash: bool, ce=None):
     """Att_Baseline.forward(mode='train') on tensor cores: every contraction a tcgen05 GEMM, the three recurrences (encoder forward,
-    encoder reverse via the direction flag, decoder) in the persistent cluster kernel.  Returns (fp32 logits [B,L-1,V], saved)."""
+    encoder reverse via the direction flag, decoder) in the persistent cluster kernel.  Returns (fp32 logits [B,L-1,V], saved); with
+    ce = dict(targets_full, loss) the vocab projection is fused with the loss (time-major bf16 logits, saved['lse'])."""
     B, Lq, F = feats.shape
     H = P["encoder.weight_hh_l0"].shape[1]
     V, E = P["embedding.weight"].shape
@@ -268,16 +275,31 @@ def att_forward_bf16(P, S, feats, targets, stash: bool):
     EB.gemm(B * Lq, H, F, xb, F, False, S["feat_linear.weight"], F, False, xproj, rowmap(Lq, H, B * H), out_bf16=True,
             bias=P["feat_linear.bias"])
     enc = {}
-    for sfx in ("", "_reverse"):
-        pre = torch.empty(Lq * B, 4 * H, device=dev)
-        EB.gemm(Lq * B, 4 * H, H, xproj, H, False, S["encoder.weight_ih_l0" + sfx], H, False, pre, dense(4 * H), bias=S["b" + sfx])
-        out = torch.empty(Lq * B, H, dtype=BF, device=dev)                         # time order for both directions
-        g = torch.empty(Lq * Bp * 4 * H, dtype=BF, device=dev) if stash else None
-        c = torch.empty(Lq * Bp * H, device=dev) if stash else None
-        EB.lstm_fwd(Lq, B, H, Lq, pre, S["b" + sfx], S["encoder.weight_hh_l0" + sfx], out, g, c, reverse=(sfx != ""))
-        ctx = torch.empty(B, H, device=dev)                                        # sum over frames (attention weights are all 1)
-        EB.colsum_bf16(out, Lq, B * H, B * H, ctx)
-        enc[sfx] = (out, g, c, EB.cast(ctx, B, H)[0])
+    cur = torch.cuda.current_stream(dev)
+    side = _side_by_side(B)
+    s_rev = EB._aux_stream(dev, "att_rev") if side else cur
+    bufs = {}
+    for sfx in ("", "_reverse"):                                                   # (allocated on the caller's stream, used on both)
+        bufs[sfx] = (torch.empty(Lq * B, 4 * H, device=dev), torch.empty(Lq * B, H, dtype=BF, device=dev),
+                     torch.empty(Lq * Bp * 4 * H, dtype=BF, device=dev) if stash else None,
+                     torch.empty(Lq * Bp * H, device=dev) if stash else None, torch.empty(B, H, device=dev),
+                     torch.empty(B, H, dtype=BF, device=dev))
+    ev0 = torch.cuda.Event()
+    ev0.record(cur)
+    for sfx, stream in (("", cur), ("_reverse", s_rev)):
+        pre, out, g, c, ctx, ctx_bf = bufs[sfx]                                    # out: time order for both directions
+        with torch.cuda.stream(stream):
+            if stream is not cur:
+                stream.wait_event(ev0)
+            EB.gemm(Lq * B, 4 * H, H, xproj, H, False, S["encoder.weight_ih_l0" + sfx], H, False, pre, dense(4 * H), bias=S["b" + sfx])
+            EB.lstm_fwd(Lq, B, H, Lq, pre, S["b" + sfx], S["encoder.weight_hh_l0" + sfx], out, g, c, reverse=(sfx != ""),
+                        tiles_per_cluster=2 if (side and sfx != "") else 1)
+            EB.colsum_bf16(out, Lq, B * H, B * H, ctx)                             # sum over frames (attention weights are all 1)
+            rc = L.load().s2vt_cast_bf16(L.stream_ptr(dev), L.ptr(ctx), L.ptr(ctx_bf), None, B, H)
+            L.check(rc, "s2vt_cast_bf16")
+        enc[sfx] = (out, g, c, ctx_bf)
+    if side:
+        cur.wait_stream(s_rev)
     Wd = S["decoder.weight_ih_l0"]
     ctx_pre = torch.empty(B, 4 * H, device=dev)
     EB.gemm(B, 4 * H, H, enc[""][3], H, False, Wd, E + 2 * H, False, ctx_pre, dense(4 * H), bias=S["b_dec"], b_off=E)
@@ -292,9 +314,15 @@ def att_forward_bf16(P, S, feats, targets, stash: bool):
     g_d = torch.empty((Lq - 1) * Bp * 4 * H, dtype=BF, device=dev) if stash else None
     c_d = torch.empty((Lq - 1) * Bp * H, device=dev) if stash else None
     EB.lstm_fwd(Lq - 1, B, H, Lq - 1, pre_d, S["b_dec"], S["decoder.weight_hh_l0"], out_d, g_d, c_d)
-    logits = torch.empty(B, Lq - 1, V, device=dev)
-    EB.gemm(R, V, H, out_d, H, False, S["out_linear.weight"], H, False, logits, rowmap(B, V, (Lq - 1) * V), bias=P["out_linear.bias"])
-    saved = dict(xb=xb, xproj=xproj, enc=enc, emb_seq=emb_seq, out_d=out_d, g_d=g_d, c_d=c_d, dims=(B, Lq, F, H, E, V)) if stash else None
+    lse = None
+    if ce is not None:
+        # row (t,b) of the time-major logits is scored against targets_full[b, t+1]
+        logits, lse = EB.vocab_ce_fwd(R, V, H, out_d, 0, S["out_linear.weight"], P["out_linear.bias"], ce["targets_full"], 1,
+                                      rowmap(B, 1, ce["targets_full"].shape[1]), ce["loss"])
+    else:
+        logits = torch.empty(B, Lq - 1, V, device=dev)
+        EB.gemm(R, V, H, out_d, H, False, S["out_linear.weight"], H, False, logits, rowmap(B, V, (Lq - 1) * V), bias=P["out_linear.bias"])
+    saved = dict(xb=xb, xproj=xproj, enc=enc, emb_seq=emb_seq, out_d=out_d, g_d=g_d, c_d=c_d, lse=lse, dims=(B, Lq, F, H, E, V)) if stash else None
     return logits, saved
 
 
@@ -338,15 +366,30 @@ def att_backward_bf16(P, S, saved, targets, dl_bf, need_dfeats: bool):
     # ---- encoder: d enc_outputs[:, l] = d context for every frame; each direction contributes to d xproj
     gWf, gbf = new(H, F), new(H)
     dfeats = new(B, Lq, F) if need_dfeats else None
+    # the two directions' BPTT sweeps side by side (second one on two tiles per cluster, see _side_by_side); the products that
+    # accumulate into shared outputs (feat_linear, dfeats) follow on the caller's stream
+    cur = torch.cuda.current_stream(dev)
+    side = _side_by_side(B)
+    s_rev = EB._aux_stream(dev, "att_rev") if side else cur
+    pre_bufs = {sfx: (new(B, H), new(Lq * B, H), torch.empty(Lq * B, 4 * H, dtype=BF, device=dev)) for sfx in ("", "_reverse")}
+    ev0 = torch.cuda.Event()
+    ev0.record(cur)
+    for sfx, col, stream in (("", E, cur), ("_reverse", E + H, s_rev)):
+        out, g, c, _ = enc[sfx]
+        dctx, dout, dg = pre_bufs[sfx]
+        with torch.cuda.stream(stream):
+            if stream is not cur:
+                stream.wait_event(ev0)
+            EB.gemm(B, H, 4 * H, dctx_pre_bf, 4 * H, False, Wd, E + 2 * H, True, dctx, dense(H), b_off=col)
+            ops.bcast_rows_f32(dctx, 0, H, B, H, Lq, dout)
+            EB.lstm_bwd(Lq, B, H, 0, dout, g, c, S["encoder.weight_hh_l0" + sfx + ".T"], dg, reverse=(sfx != ""),
+                        tiles_per_cluster=2 if (side and sfx != "") else 1)
+    if side:
+        cur.wait_stream(s_rev)
     for i, (sfx, col) in enumerate((("", E), ("_reverse", E + H))):
         out, g, c, _ = enc[sfx]
         rev = sfx != ""
-        dctx = new(B, H)
-        EB.gemm(B, H, 4 * H, dctx_pre_bf, 4 * H, False, Wd, E + 2 * H, True, dctx, dense(H), b_off=col)
-        dout = new(Lq * B, H)
-        ops.bcast_rows_f32(dctx, 0, H, B, H, Lq, dout)
-        dg = torch.empty(Lq * B, 4 * H, dtype=BF, device=dev)
-        EB.lstm_bwd(Lq, B, H, 0, dout, g, c, S["encoder.weight_hh_l0" + sfx + ".T"], dg, reverse=rev)
+        dg = pre_bufs[sfx][2]
         gWih, gWhh = new(4 * H, H), new(4 * H, H)
         EB.gemm(4 * H, H, Lq * B, dg, 4 * H, True, xproj, H, True, gWih, dense(H))
         # previous hidden state in PROCESSING order: time t-1 for the forward direction, t+1 for the reverse one
@@ -388,6 +431,32 @@ class _AttTrainBf16Fn(torch.autograd.Function):
         dl_tm.view(Lm1, B, V).copy_(dl.transpose(0, 1))
         G, dfeats = att_backward_bf16(ctx.P, ctx.S, ctx.saved, ctx.targets, dl_tm, ctx.needs_input_grad[1])
         ctx.saved = None
+        return (None, dfeats, None) + tuple(G[k] for k in ATT_PARAM_ORDER)
+
+
+class _AttLossBf16Fn(torch.autograd.Function):
+    """Fused forward + MaskCriterion (utils.py:13-26) for Att_Baseline: the vocab projection's epilogue reduces the loss statistics,
+    the logits are written once as bf16 and turned into dL/dlogits in place (same kernels as S2VT.forward_loss)."""
+
+    @staticmethod
+    def forward(ctx, module, feats, targets_full, *params):
+        P = dict(zip(ATT_PARAM_ORDER, params))
+        need = any(ctx.needs_input_grad)
+        ctx.S = module._shadow.get(P)
+        Lq = feats.shape[1]
+        tin = targets_full[:, :Lq - 1].contiguous()
+        loss = torch.empty((), device=feats.device)
+        logits, saved = att_forward_bf16(P, ctx.S, feats, tin, stash=need, ce=dict(targets_full=targets_full, loss=loss))
+        ctx.saved, ctx.P, ctx.tin, ctx.tfull, ctx.logits = saved, P, tin, targets_full, logits
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        B, Lq, F, H, E, V = ctx.saved["dims"]
+        g = gloss.contiguous().to(torch.float32)
+        dl = EB.ce_dlogits_inplace(ctx.logits, (Lq - 1) * B, V, ctx.saved["lse"], ctx.tfull, 1, rowmap(B, 1, ctx.tfull.shape[1]), g)
+        G, dfeats = att_backward_bf16(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1])
+        ctx.saved = ctx.logits = None
         return (None, dfeats, None) + tuple(G[k] for k in ATT_PARAM_ORDER)
 
 
@@ -449,6 +518,26 @@ class Att_Baseline(nn.Module):
     def _params(self) -> Dict[str, torch.Tensor]:
         sd = dict(self.named_parameters())
         return {k: sd[k] for k in ATT_PARAM_ORDER}
+
+    # ---- data-parallel trainer hooks (dp.DataParallelTrainer): one gradient bucket, private bf16 weight copies
+    DP_BUCKETS = (("all", ATT_PARAM_ORDER),)
+
+    def _needs_derived_shadows(self) -> bool:
+        return False
+
+    def forward_loss(self, feats, targets, mask=None):
+        """criterion(model(feats, targets[:, :-1], 'train'), targets, mask) (train.py:120-122 with Att_Baseline, attention_baseline.py:
+        59-84) as one scalar, without handing [B,L-1,V] logits to autograd.  Tensor-core path only (the exact path goes through
+        forward(mode='train') + MaskCriterion)."""
+        self._check(feats)
+        if targets.dim() != 2 or targets.shape[1] < self.length:
+            raise RuntimeError("targets must be [B, >= length] (got %s)" % (tuple(targets.shape),))
+        P = self._params()
+        if not self._use_bf16():
+            from .criterion import MaskCriterion
+            m = mask if mask is not None else torch.ones_like(targets, dtype=torch.float32)
+            return MaskCriterion()(self(feats, targets=targets[:, :-1], mode="train"), targets[:, :self.length], m[:, :self.length])
+        return _AttLossBf16Fn.apply(self, feats.contiguous(), targets[:, :self.length].contiguous().to(torch.int64), *[P[k] for k in ATT_PARAM_ORDER])
 
     def _check(self, feats):
         if feats.dim() != 3 or feats.shape[1] != self.length or feats.shape[2] != self.dim_feat:

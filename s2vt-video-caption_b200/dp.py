@@ -27,12 +27,13 @@ BUCKETS: Tuple[Tuple[str, Tuple[str, ...]], ...] = (
 )
 
 
-def bucket_ranges(names: Sequence[str], offsets: Sequence[int], sizes: Sequence[int]) -> Dict[str, Tuple[int, int]]:
+def bucket_ranges(names: Sequence[str], offsets: Sequence[int], sizes: Sequence[int], buckets=None) -> Dict[str, Tuple[int, int]]:
     """Contiguous [begin, end) element range of each bucket inside the flat gradient buffer.  Raises if a bucket's
-    tensors are not adjacent (they are, for the reference's registration order)."""
+    tensors are not adjacent (they are, for the reference's registration order).  `buckets`: ((name, members), ...), default the
+    S2VT module's BUCKETS; a model may bring its own as `DP_BUCKETS` (Att_Baseline)."""
     pos = {n: (o, o + s) for n, o, s in zip(names, offsets, sizes)}
     out = {}
-    for bname, members in BUCKETS:
+    for bname, members in (buckets if buckets is not None else BUCKETS):
         spans = sorted(pos[m] for m in members)
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
             if b0 - a1 > 7:                      # alignment padding only
@@ -119,7 +120,7 @@ class GradAllReducer:
                 self.pending.append((work, view))
 
     def finish(self) -> None:
-        for bname, _ in BUCKETS:
+        for bname in self.ranges:
             if bname not in self.done:
                 self.ready(bname)
         if self.overlap:
@@ -140,7 +141,7 @@ class DataParallelTrainer:
         f = optimizer._ensure_flat()
         names = [n for n, _ in model.named_parameters()]
         sizes = [p.numel() for p in f["params"]]
-        self.ranges = bucket_ranges(names, f["offsets"], sizes)
+        self.ranges = bucket_ranges(names, f["offsets"], sizes, getattr(model, "DP_BUCKETS", None))
         self.reducer = GradAllReducer(f["g"], self.ranges, group=group, overlap=overlap)
         # Adam per bucket, right behind that bucket's all-reduce: needs gradients that backward writes in place (CUDA path)
         self.early_adam = f["g"].is_cuda
@@ -194,10 +195,19 @@ class DataParallelTrainer:
             with torch.cuda.stream(self._adam_stream):
                 self._adam_stream.wait_event(ev)
                 self.opt.step_range(a, b)
-                self.opt.refresh_derived(bucket)
+                if self._needs_derived():
+                    self.opt.refresh_derived(bucket)
         else:
             self.opt.step_range(a, b)
-            self.opt.refresh_derived(bucket)
+            if self._needs_derived():
+                self.opt.refresh_derived(bucket)
+
+    def _needs_derived(self) -> bool:
+        """Does the model's engine read the optimizer-maintained bf16 shadows / derived weight forms (engine_bf16)?  Engines that cast
+        their own private copies at the head of every step (engine_step, Att_Baseline) do not, and their captured steps need no
+        'shadows are current' precondition."""
+        fn = getattr(self.model, "_needs_derived_shadows", None)
+        return True if fn is None else bool(fn())
 
     # ---- input buffers
     def input_buffers(self, feats_shape, targets_shape, dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -267,7 +277,8 @@ class DataParallelTrainer:
         # If anything else touched the weights since (load_state_dict, an in-place edit, another optimizer), run this step eagerly: it
         # re-derives them from the fp32 masters and leaves everything current again.
         f = self.opt._flat
-        if f.get("shadow_state") != (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"])) or not f.get("derived_ok"):
+        if self._needs_derived() and (f.get("shadow_state") != (ops.WEIGHT_EPOCH, tuple(p._version for p in f["params"])) or
+                                      not f.get("derived_ok")):
             self._eager_steps += 1
             return self._step_eager(feats, targets, mask)
         if self._eager_steps < 2 or feats.requires_grad:         # (feats.grad belongs to the caller's tensor: no static copy of it)

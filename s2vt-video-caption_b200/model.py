@@ -465,6 +465,9 @@ class S2VT(nn.Module):
             return ES
         return None
 
+    def _needs_derived_shadows(self) -> bool:
+        return self._bf16_engine() is EB         # engine_step casts private copies at the head of every step (dp.DataParallelTrainer)
+
     def _engine_and_shadows(self, P):
         eng = self._bf16_engine()
         if eng is EB:

@@ -147,3 +147,46 @@ def test_att_bf16_train_vs_reference_golden(dev, name):
                 continue
             n = np.linalg.norm(gv.astype(np.float64))
             assert abs(n - g["grad_norm/" + k]) <= 3e-2 * g["grad_norm/" + k] + 1e-12, (k, n, g["grad_norm/" + k])
+
+
+def test_att_forward_loss_and_trainer_graph_replay(dev):
+    """Att_Baseline gets the S2VT module's treatment: fused forward_loss (same loss / gradients as module + MaskCriterion), and
+    DataParallelTrainer steps that replay one CUDA graph (two encoder sweeps side by side, private bf16 weight copies)."""
+    from s2vt_b200.dp import DataParallelTrainer
+    V, F, H, E, Lq, B = 203, 64, 128, 64, 8, 6
+    torch.manual_seed(21)
+    m1 = s2vt_b200.Att_Baseline(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    m2 = s2vt_b200.Att_Baseline(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+    m2.load_state_dict(m1.state_dict())
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, Lq, F, generator=g).to(dev)
+    targets = torch.randint(1, V, (B, Lq), generator=g).to(dev)
+    mask = torch.ones(B, Lq, device=dev)
+    la = s2vt_b200.MaskCriterion()(m1(feats, targets=targets[:, :-1], mode="train"), targets, mask)
+    la.backward()
+    lb = m2.forward_loss(feats, targets, mask)
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 2e-3 * abs(la.item())
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        if a.grad.abs().max() == 0:
+            assert b.grad.abs().max() == 0, k
+            continue
+        rel = (a.grad - b.grad).norm().item() / a.grad.norm().item()
+        assert rel <= 2e-2, (k, rel)
+    del la, lb
+    out = {}
+    for graph in (False, True):
+        torch.manual_seed(22)
+        m = s2vt_b200.Att_Baseline(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+        opt = s2vt_b200.FusedAdam(m.parameters(), lr=1e-3)
+        tr = DataParallelTrainer(m, opt, cuda_graph=graph)
+        losses = [float(tr.step(feats, targets).item()) for _ in range(6)]
+        tr.check_device_errors()
+        assert (tr.replays >= 3) == graph
+        out[graph] = (losses, {k: p.detach().clone() for k, p in m.named_parameters()})
+    for a, b in zip(out[True][0], out[False][0]):
+        assert abs(a - b) <= 2e-3 * abs(b), (out[True][0], out[False][0])
+    assert out[False][0][-1] < out[False][0][0]
+    for k in out[True][1]:
+        a, b = out[True][1][k].double(), out[False][1][k].double()
+        assert (a - b).norm().item() <= 2e-3 * max(1e-30, b.norm().item()), k

@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: Att_Baseline (attention_baseline.py) training throughput on one GPU or data-parallel under torchrun.
-One step = zero_grad + forward(mode='train') + MaskCriterion + backward + (gradient all-reduce) + FusedAdam.step, batch 64/GPU,
-MSVD shape (80 x 4096 features, V = 13000, H = E = 512), synthetic data, random-init weights.  Prints one JSON line.
+One step = zero_grad + forward + MaskCriterion + backward + (gradient all-reduce) + Adam, batch 64/GPU, MSVD shape (80 x 4096
+features, V = 13000, H = E = 512), synthetic data, random-init weights.  Default: DataParallelTrainer (fused forward_loss, one
+all-reduce bucket, CUDA-graph replay); --api times the unchanged loop body (module forward + MaskCriterion + backward + step).
+Prints one JSON line.
 
-    python tools/bench_att.py [--steps 10] [--precision bf16|fp32]
+    python tools/bench_att.py [--steps 20] [--precision bf16|fp32] [--api]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_att.py
 """
 import argparse
 import json
@@ -22,7 +25,8 @@ from bench import CFG, synth_batch
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--api", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
     args = ap.parse_args()
@@ -30,7 +34,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = s2vt_b200.Att_Baseline(CFG["V"], CFG["F"], CFG["L"], dim_hid=CFG["H"], dim_embed=CFG["E"], train_precision=args.precision).to(dev)
@@ -39,8 +44,17 @@ def main():
     flat_g = None
     batches = [synth_batch(CFG["B"], 99 + rank * 10 + i, device=dev) for i in range(3)]
 
+    from s2vt_b200.dp import DataParallelTrainer
+    trainer = None
+    if not args.api and args.precision != "fp32":
+        trainer = DataParallelTrainer(model, opt)
+        for f, t, _ in batches:
+            trainer.register_inputs(f, t)
+
     def step(i):
         f, t, m = batches[i % 3]
+        if trainer is not None:
+            return trainer.step(f, t, m)
         opt.zero_grad(set_to_none=True)
         loss = crit(model(f, targets=t[:, :-1], mode="train"), t, m)
         loss.backward()
@@ -50,7 +64,7 @@ def main():
         opt.step()
         return loss
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 6)):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
@@ -68,8 +82,11 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "Att_Baseline train videos/sec", "value": round(world * CFG["B"] / (ms / 1e3), 1), "ms_per_step": round(ms, 3),
                           "n_gpus": world, "precision": args.precision, "batch_per_gpu": CFG["B"], "loss": float(loss.item()),
+                          "path": "DataParallelTrainer (forward_loss, graph replays %d)" % trainer.replays if trainer is not None else "module + MaskCriterion + FusedAdam.step, eager",
                           "launches_total": int(s2vt_b200.launch_count())}))
     if world > 1:
+        if trainer is not None:
+            trainer.release_graphs()
         dist.destroy_process_group()
 
 
