@@ -137,7 +137,7 @@ def train_forward(P, S, feats, targets, stash: bool, batch_major_logits: bool, c
 
 
 def train_backward(P, S, saved, targets, dl_bf: torch.Tensor, need_dfeats: bool, gout: Optional[Dict[str, torch.Tensor]] = None,
-                   on_ready=None):
+                   on_ready=None, early_out_wgrad: bool = False):
     """BPTT for train_forward; same contract as engine_bf16.train_backward (dl_bf: bf16 [(L-1)B, V] time-major, row pitch % 8 == 0).
     The bf16 weight copies are private to this engine, so a bucket is released (all-reduce + Adam may touch its fp32 masters) as soon
     as its gradients are complete."""

@@ -324,7 +324,8 @@ class _TrainLossFn(torch.autograd.Function):
         direct, cb = _direct_grad_targets(ctx.module)
         if ctx.bf16:
             dl = EB.ce_dlogits_inplace(logits, (L - 1) * B, V, ctx.saved["lse"], ctx.tfull, 1, rowmap(B, 1, L), g)
-            G = ctx.eng.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb)
+            G = ctx.eng.train_backward(ctx.P, ctx.S, ctx.saved, ctx.tin, dl, ctx.needs_input_grad[1], gout=direct, on_ready=cb,
+                                       early_out_wgrad=cb is not None and getattr(ctx.module, "_dp_world", 1) > 1)
             grads, dfeats = [G[k] for k in PARAM_ORDER], G.get("feats")
         else:
             scratch = torch.empty((), device=logits.device)
