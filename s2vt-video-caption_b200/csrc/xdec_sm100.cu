@@ -69,7 +69,8 @@ struct XParams {
   unsigned long long* o_key;                                   // ARGMAX: per-row packed (value, index) maximum, zeroed by the consumer
   // LSTM: the previous step's argmax keys -> token (gidx == nullptr); n-tile 0 records it and clears the keys of the next step
   const unsigned long long* key_in; unsigned long long* key_clear; int64_t* tok_out; long long tok_ld;
-  unsigned long long* trace;   // debug: 8 %globaltimer stamps of CTA (0,0) (tools/trace_xdec.py), or nullptr
+  unsigned long long* trace;   // debug: 8 %globaltimer stamps of one CTA (tools/trace_xdec.py), or nullptr
+  int trace_bx, trace_by;      // which CTA (default (0,0); S2VT_XDEC_TRACE_CTA=x,y clamps to the grid)
 };
 
 // Programmatic dependent launch: a step kernel is launched while its predecessor in the stream still runs; everything that
@@ -148,7 +149,7 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int tile_m = p.m_fastest ? blockIdx.x : blockIdx.y, tile_n = p.m_fastest ? blockIdx.y : blockIdx.x;
   const int n_tiles = p.m_fastest ? gridDim.y : gridDim.x;
   const int m0 = tile_m * BM, n0 = tile_n * BN;
-  unsigned long long* const trace = (p.trace && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+  unsigned long long* const trace = (p.trace && blockIdx.x == min(p.trace_bx, (int)gridDim.x - 1) && blockIdx.y == min(p.trace_by, (int)gridDim.y - 1)) ? p.trace : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = ptx::globaltimer_ns();
 
   if (warp_idx == 0 && ptx::elect_one()) {
@@ -704,6 +705,194 @@ __global__ void beam_gather_kernel(int S, int HP, const int* __restrict__ parent
   }
 }
 
+// ---- one depth's bookkeeping in ONE kernel: a CTA per video, a warp per beam slot.
+//   1. every warp merges its slot's per-tile partials into the slot's best kc (log-prob, token) pairs (beam_combine_kernel's code)
+//   2. thread 0 runs the PriorityQueue step for the video (beam_select_kernel's code) on the candidates in shared memory
+//   3. every warp builds its NEW slot: token history, answer so far, and the LSTM state copied from the parent slot (the code of
+//      beam_hist_kernel and beam_gather_kernel); the candidate bounds of the next depth are reset
+// Replaces four launches per depth (merge 28 us, queue 12 us, histories 5 us, re-order 9 us when run one after the other).
+__global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int eos, int HP, int n_part, const float* __restrict__ len_pen,
+                                   BeamMeta old_, BeamMeta new_, const float* __restrict__ ms, const float* __restrict__ tv,
+                                   const int* __restrict__ ti, int* __restrict__ nbeam, int* __restrict__ done, int* __restrict__ n_done,
+                                   int64_t* __restrict__ out_tokens, int* __restrict__ out_len,
+                                   __half* __restrict__ a1, long long a1_plane, __half* __restrict__ x, long long x_plane,
+                                   const __half* __restrict__ h2n, long long h2n_plane,
+                                   float* __restrict__ c1, const float* __restrict__ c1n, float* __restrict__ c2, const float* __restrict__ c2n,
+                                   unsigned int* __restrict__ row_thr) {
+  extern __shared__ float sh_all[];
+  __shared__ float s_lp[KC * KC];
+  __shared__ int s_tok[KC * KC];
+  __shared__ int s_parent[KC], s_was_done;
+  const int v = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = v * bw, s = base + w;
+  const int n = n_part * KC;
+  const bool was_done = done[v] != 0;              // (read by every thread before thread 0 may set it below: barrier in between)
+  __shared__ float m_key[KC], m_pen[KC];
+  __shared__ int m_tok[KC], m_len[KC], m_fin[KC], m_nb;
+  if (threadIdx.x < bw) {                          // the video's queue state, fetched in parallel for the serial step below
+    const int q = base + threadIdx.x;
+    m_key[threadIdx.x] = old_.key[q]; m_tok[threadIdx.x] = old_.tok[q]; m_len[threadIdx.x] = old_.len[q]; m_fin[threadIdx.x] = old_.fin[q];
+    m_pen[threadIdx.x] = len_pen[old_.len[q] + 1];
+    if (threadIdx.x == 0) m_nb = nbeam[v];
+  }
+  // ---- 1. merge (skipped for a finished video: its candidates are never looked at)
+  if (!was_done) {
+    float mx = -INFINITY;
+    for (int j = lane; j < n_part; j += 32) mx = fmaxf(mx, ms[2 * ((long long)s * n_part + j)]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < n_part; j += 32) {
+      const long long o = 2 * ((long long)s * n_part + j);
+      sum += ms[o + 1] * expf(ms[o] - mx);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float logsum = logf(sum);
+    float* shv = sh_all + (size_t)w * 2 * n;
+    int* shi = reinterpret_cast<int*>(shv + n);
+    // (eight independent loads in flight per lane and array: the loop is otherwise one L2 round trip per iteration)
+    for (int j0 = lane; j0 < n; j0 += 32 * 8) {
+      int ids[8];
+      float vs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j0 + 32 * u;
+        ids[u] = jj < n ? __ldcg(ti + (long long)s * n + jj) : 0x7fffffff;
+        vs[u] = jj < n ? __ldcg(tv + (long long)s * n + jj) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = j0 + 32 * u;
+        if (jj < n) { shi[jj] = ids[u]; shv[jj] = vs[u]; }
+      }
+    }
+    __syncwarp();
+    float lv[KC];
+    int li[KC];
+#pragma unroll
+    for (int q = 0; q < KC; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
+    for (int j = lane; j < n; j += 32) {
+      const int id = shi[j];
+      if (id == 0x7fffffff) continue;
+      const float val = shv[j];
+      if (val > lv[KC - 1] || (val == lv[KC - 1] && id < li[KC - 1])) {
+        lv[KC - 1] = val; li[KC - 1] = id;
+#pragma unroll
+        for (int q = KC - 1; q > 0; --q) {
+          if (lv[q] > lv[q - 1] || (lv[q] == lv[q - 1] && li[q] < li[q - 1])) {
+            const float fv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = fv;
+            const int iv = li[q]; li[q] = li[q - 1]; li[q - 1] = iv;
+          }
+        }
+      }
+    }
+    for (int r = 0; r < kc; ++r) {
+      float bv = lv[0];
+      int bi = li[0], bl = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bl = ol; }
+      }
+      if (lane == 0) {
+        s_lp[w * KC + r] = (bv - mx) - logsum;                    // log_softmax as torch computes it: (z - max) - log(sum exp)
+        s_tok[w * KC + r] = bi != 0x7fffffff ? bi : 0;
+      }
+      if (lane == bl && bi != 0x7fffffff) {
+#pragma unroll
+        for (int q = 0; q < KC - 1; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
+        lv[KC - 1] = -INFINITY; li[KC - 1] = 0x7fffffff;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 2. the PriorityQueue step of S2VTModel.py:186-238 (see beam_select_kernel)
+  if (threadIdx.x == 0) {
+    s_was_done = was_done ? 1 : 0;
+    if (was_done) {
+      for (int j = 0; j < bw; ++j) {
+        const int q = base + j;
+        new_.key[q] = m_key[j]; new_.tok[q] = m_tok[j]; new_.len[q] = m_len[j]; new_.fin[q] = m_fin[j];
+        s_parent[j] = q;
+      }
+    } else {
+      const int nb = m_nb;
+      int ptr[KC];
+      long long count = 0;
+      for (int j = 0; j < nb; ++j) { ptr[j] = 0; count += m_fin[j] ? 1 : topk; }
+      const bool last = (count <= bw);
+      const int take = count < bw ? (int)count : bw;
+      for (int r = 0; r < take; ++r) {
+        float bestk = INFINITY; int bj = -1;
+        for (int j = 0; j < nb; ++j) {
+          float k;
+          if (m_fin[j]) { if (ptr[j] > 0) continue; k = m_key[j]; }
+          else {
+            if (ptr[j] >= kc) continue;
+            k = -(s_lp[j * KC + ptr[j]] / m_pen[j]);
+          }
+          if (bj < 0 || k < bestk) { bestk = k; bj = j; }
+        }
+        const int d = base + r;
+        if (bj < 0) {
+          new_.key[d] = INFINITY; new_.tok[d] = 0; new_.len[d] = 1; new_.fin[d] = 0; s_parent[r] = d;
+          continue;
+        }
+        const int q = base + bj;
+        const int ln = m_len[bj];
+        if (m_fin[bj]) {
+          new_.key[d] = m_key[bj]; new_.tok[d] = m_tok[bj]; new_.len[d] = ln; new_.fin[d] = 1;
+        } else {
+          const int tk = s_tok[bj * KC + ptr[bj]];
+          new_.key[d] = bestk; new_.tok[d] = tk; new_.len[d] = ln + 1; new_.fin[d] = (tk == eos) ? 1 : 0;
+        }
+        ptr[bj] += 1;
+        s_parent[r] = q;
+        if (r == 0) out_len[v] = new_.len[d];
+      }
+      for (int r = take; r < bw; ++r) {
+        const int d = base + r;
+        new_.key[d] = INFINITY; new_.tok[d] = 0; new_.len[d] = 1; new_.fin[d] = 0;
+        s_parent[r] = d;
+      }
+      nbeam[v] = take;
+      if (last) { done[v] = 1; atomicAdd(n_done, 1); }
+    }
+    __threadfence_block();
+  }
+  __syncthreads();
+  // ---- 3. the new slot d = base + w: history, answer so far, state from its parent
+  const int d = s;
+  if (lane < KC) row_thr[(long long)d * KC + lane] = 0u;            // next depth's candidate bounds start from "none"
+  if (s_was_done) return;                                           // frozen: outputs final; its state buffers keep finite values
+  const int ps = s_parent[w];
+  {
+    const bool unused = (new_.key[d] == INFINITY);
+    const bool fresh = !unused && !m_fin[ps - base];
+    const int Ln = new_.len[d];
+    for (int q = lane; q < D1; q += 32) {
+      int t = unused ? -1 : old_.hist[(long long)ps * D1 + q];
+      if (fresh && q == Ln - 1) t = new_.tok[d];
+      new_.hist[(long long)d * D1 + q] = t;
+      if (w == 0) out_tokens[(long long)v * D1 + q] = (q < Ln) ? t : -1;
+    }
+  }
+  for (int u = lane; u < HP; u += 32) {
+    a1[(long long)d * HP + u] = x[(long long)ps * 2 * HP + u];
+    a1[a1_plane + (long long)d * HP + u] = x[x_plane + (long long)ps * 2 * HP + u];
+    c1[(long long)d * HP + u] = c1n[(long long)ps * HP + u];
+    c2[(long long)d * HP + u] = c2n[(long long)ps * HP + u];
+  }
+  // (x[:, HP:] is written for slot d while another warp may still read x[:, :HP] of slot d as ITS parent: different columns)
+  for (int u = lane; u < HP; u += 32) {
+    x[(long long)d * 2 * HP + HP + u] = h2n[(long long)ps * HP + u];
+    x[x_plane + (long long)d * 2 * HP + HP + u] = h2n[h2n_plane + (long long)ps * HP + u];
+  }
+}
+
 // slot 0 of each video <- the video's encode state; the other slots start from zero
 __global__ void beam_state_init_kernel(int B, int bw, int HP, const __half* __restrict__ h1, long long h1_plane, const float* __restrict__ c1e,
                                        const __half* __restrict__ h2, long long h2_plane, const float* __restrict__ c2e,
@@ -746,6 +935,9 @@ static int launch_x(cudaStream_t st, int M, int N, int K, const Planes& A, const
   p.a_inv = A.inv; p.b_inv = B.inv;
   if (g_trace_buf && g_trace_n < g_trace_max) {
     p.trace = g_trace_buf + 8 * (size_t)g_trace_n++;
+    static int tbx = -1, tby = 0;
+    if (tbx < 0) { const char* e = getenv("S2VT_XDEC_TRACE_CTA"); tbx = 0; if (e) sscanf(e, "%d,%d", &tbx, &tby); }
+    p.trace_bx = tbx; p.trace_by = tby;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -1226,20 +1418,30 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
   const Planes WH1{W.hh1, HP, (long long)G * HP, W.inv + INV_HH1}, WC2{W.cat2, 2 * HP, (long long)G * 2 * HP, W.inv + INV_CAT2};
   const Planes WO{W.out, HP, (long long)g.V * HP, W.inv + INV_OUT};
   const int n_part2 = 2 * ceil_div(g.V, 128);                 // candidate lists per row: one per tile and epilogue warp group
-  const size_t combine_smem = (size_t)2 * n_part2 * KC * 8;
-  S2VT_REQUIRE(combine_smem <= 200 * 1024, "s2vt_xdec_beam: vocabulary too large for the candidate merge (V <= 102400)");
-  if (combine_smem > 48 * 1024)
-    S2VT_CHECK_CUDA(cudaFuncSetAttribute(beam_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const size_t finish_smem = (size_t)beam_width * n_part2 * KC * 8;      // per slot: the row's candidates (values + indices)
+  S2VT_REQUIRE(finish_smem <= 200 * 1024, "s2vt_xdec_beam: vocabulary x beam width too large for the candidate merge (%zu bytes of shared memory)", finish_smem);
+  if (finish_smem > 48 * 1024)
+    S2VT_CHECK_CUDA(cudaFuncSetAttribute(beam_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  // keep the SMs' shared-memory carve-out where the GEMM kernels around it need it (a different carve-out drains the SM first)
+  S2VT_CHECK_CUDA(cudaFuncSetAttribute(beam_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int chunk = 0;
+  // S2VT_XDEC_EVENTS=1 (debug): CUDA events around the four kernels of depth 10, printed after the call
+  static int want_events = -1;
+  if (want_events < 0) { const char* e = getenv("S2VT_XDEC_EVENTS"); want_events = (e && e[0] == '1') ? 1 : 0; }
+  cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (want_events) for (int i = 0; i < 5; ++i) cudaEventCreate(&tev[i]);
+#define X_STAMP(i) do { if (want_events && depth == 10) cudaEventRecord(tev[i], st); } while (0)
   for (int depth = 0; depth < max_depth; ++depth) {
     const xd::BeamMeta& mo = w.meta[depth & 1];
     const xd::BeamMeta& mn = w.meta[(depth + 1) & 1];
+    X_STAMP(0);
     {   // vid_rnn step on the zero pad (S2VTModel.py:208-210): h1' -> x[:, :HP]
       StepArgs a{};
       a.bias = W.b1; a.c_in = w.c1; a.c_out = w.c1n; a.hp = w.x; a.hp_ld = 2 * HP; a.hp_plane = 2 * SH;
       Planes A{w.a1, HP, SH, W.inv + INV_H};
       X_TRY(x_lstm_step(st, S, HP, HP, A, WH1, a));
     }
+    X_STAMP(1);
     {   // word_rnn step on [embed(word) | vid_out] (S2VTModel.py:207,211-212): K runs over [h1' | h2]
       StepArgs a{};
       a.bias = W.b2; a.gtab = W.ew; a.gtab_ld = G; a.gidx = mo.tok;
@@ -1247,6 +1449,7 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
       Planes A{w.x, 2 * HP, 2 * SH, W.inv + INV_H};
       X_TRY(x_lstm_step(st, S, HP, 2 * HP, A, WC2, a));
     }
+    X_STAMP(2);
     {   // out_linear + log_softmax + top-k partials (S2VTModel.py:213-216)
       XParams p{};
       p.bias = W.bout; p.o_ms = w.ms; p.o_val = w.tv; p.o_idx = w.ti;
@@ -1254,15 +1457,12 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
       Planes A{w.h2n, HP, SH, W.inv + INV_H};
       X_TRY((launch_x<128, EPI_BEAM>(st, S, g.V, HP, A, WO, p)));
     }
-    beam_combine_kernel<<<ceil_div(S, 2), 64, combine_smem, st>>>(S, n_part2, kc, w.ms, w.tv, w.ti, w.cand_lp, w.cand_tok);
+    X_STAMP(3);
+    beam_finish_kernel<<<B, 32 * beam_width, finish_smem, st>>>(B, beam_width, topk, kc, D1, g.eos, HP, n_part2, len_pen, mo, mn, w.ms, w.tv, w.ti,
+                                                                  w.nbeam, w.done, w.n_done, out_tokens, out_len, w.a1, SH, w.x, 2 * SH, w.h2n, SH,
+                                                                  w.c1, w.c1n, w.c2, w.c2n, w.row_thr);
     S2VT_CHECK_LAUNCH();
-    beam_select_kernel<<<ceil_div(B, 32), 32, 0, st>>>(B, beam_width, topk, kc, D1, g.eos, len_pen, mo, mn, w.cand_lp, w.cand_tok,
-                                                      w.nbeam, w.done, w.was_done, w.parent, out_len, w.n_done);
-    S2VT_CHECK_LAUNCH();
-    beam_hist_kernel<<<S, 32, 0, st>>>(beam_width, D1, mo, mn, w.parent, w.was_done, out_tokens);
-    S2VT_CHECK_LAUNCH();
-    beam_gather_kernel<<<dim3(S, 4), 128, 0, st>>>(S, HP, w.parent, w.a1, SH, w.x, 2 * SH, w.h2n, SH, w.c1, w.c1n, w.c2, w.c2n, w.row_thr);
-    S2VT_CHECK_LAUNCH();
+    X_STAMP(4);
     if (check_every > 0 && (depth + 1) % check_every == 0 && depth + 1 < max_depth) {
       // Early exit without draining the stream: the count of finished videos after this chunk of depths goes to a pinned slot, and the
       // host waits for the PREVIOUS chunk's count before it enqueues the next one -- one chunk is always queued behind the running
@@ -1278,6 +1478,15 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
       ++chunk;
     }
   }
+  if (want_events && max_depth > 10) {
+    cudaStreamSynchronize(st);
+    float ms[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
+    fprintf(stderr, "[xdec beam depth 10] vid_rnn step %.1f us, word_rnn step %.1f us, vocab + top-k %.1f us, queue/merge/re-order %.1f us\n",
+            1e3f * ms[0], 1e3f * ms[1], 1e3f * ms[2], 1e3f * ms[3]);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(tev[i]);
+  }
+#undef X_STAMP
   return 0;
 }
 #undef X_TRY
