@@ -338,12 +338,14 @@ int s2vt_ce_dlogits_inplace_bf16(void* stream, void* logits_bf16, int64_t R, int
  * H = 1000).  Time-major layouts, row = t*B + b:
  *   pre [n_pre,B,4H] f32 and gates [T,B,4H] bf16 have their columns INTERLEAVED (4u+g); w_hh_il = W_hh with rows interleaved alike;
  *   dgates [T,B,4H] bf16 comes out in natural gate order (g*H+u), the layout of the time-batched weight-gradient products;
- *   w_hh_t = W_hh^T [H,4H] bf16;  cells [T,B,H] f32;  out [T,B,H] bf16;  dc_ws [B,H] f32 scratch.
+ *   w_hh_t = W_hh^T [H,4H] bf16;  cells [T,B,H] f32;  out [T,B,H] bf16;  ws >= s2vt_lstm_steps_bwd_ws_bytes(B,H) scratch
+ *   (running dL/dc, split-K partial sums: the backward product, K = 4H over few tiles, is split until the step fills the machine).
  * replaces: nn.LSTM (S2VTModel.py:19-22,67,77) and its autograd (train.py:124). */
 int s2vt_lstm_steps_fwd_bf16(void* stream, int T, int B, int H, int n_pre, const float* pre, const float* bias_il,
                              const void* w_hh_il, void* out, void* gates, float* cells);
+int64_t s2vt_lstm_steps_bwd_ws_bytes(int B, int H);
 int s2vt_lstm_steps_bwd_bf16(void* stream, int T, int B, int H, int dout_t0, const float* dout, const void* gates,
-                             const float* cells, const void* w_hh_t, void* dgates, float* dc_ws);
+                             const float* cells, const void* w_hh_t, void* dgates, void* ws);
 
 /* ------------------------------------------------------------------ exact-grade decode on the tensor cores ("x" path)
  * fp32 operands are scaled by a power of two and split into two fp16 planes (hi, lo); a product is three

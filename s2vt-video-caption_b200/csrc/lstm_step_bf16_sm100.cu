@@ -40,6 +40,9 @@ struct StepParams {
   // backward (N = H)
   const float* dout; const __nv_bfloat16* gates; const float* c_t; const float* c_prev;
   float* dc; __nv_bfloat16* dgates;
+  // backward split-K: gridDim.z CTAs share a tile, each over kb_per_split K blocks; partial sums meet in `part` [z][M][N] and the
+  // last CTA of a tile to arrive (tile_count, self-resetting) adds them up and runs the epilogue
+  int kb_per_split; float* part; unsigned int* tile_count;
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -55,6 +58,10 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb0 = (EPI == EPI_BWD && gridDim.z > 1) ? (int)blockIdx.z * p.kb_per_split : 0;
+  const int kb1 = (EPI == EPI_BWD && gridDim.z > 1) ? min(p.num_kb, kb0 + p.kb_per_split) : p.num_kb;
+  const int nkb = kb1 - kb0;                             // K blocks of this CTA
+  __shared__ int s_last;
 
   if (warp_idx == 0 && ptx::elect_one() && p.num_kb > 0) {
     ptx::prefetch_tmap(&tmA);
@@ -81,40 +88,40 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp_idx == 0) {
     if (ptx::elect_one()) {
       // weight tiles first (they do not depend on the previous step), the state operand after the dependency resolves
-      const int npre = p.num_kb < STAGES ? p.num_kb : STAGES;
-      for (int kb = 0; kb < npre; ++kb) {
-        const uint32_t fb = ptx::smem_u32(&full_bar[kb]);
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < npre; ++i) {
+        const uint32_t fb = ptx::smem_u32(&full_bar[i]);
         ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-        ptx::tma_load_2d(smem_base + kb * STAGE_BYTES + A_BYTES, &tmB, fb, kb * BK, n0);
+        ptx::tma_load_2d(smem_base + i * STAGE_BYTES + A_BYTES, &tmB, fb, (kb0 + i) * BK, n0);
       }
       pdl_wait();
-      for (int kb = 0; kb < npre; ++kb)
-        ptx::tma_load_2d(smem_base + kb * STAGE_BYTES, &tmA, ptx::smem_u32(&full_bar[kb]), kb * BK, m0);
-      for (int kb = npre; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int i = 0; i < npre; ++i)
+        ptx::tma_load_2d(smem_base + i * STAGE_BYTES, &tmA, ptx::smem_u32(&full_bar[i]), (kb0 + i) * BK, m0);
+      for (int i = npre; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         if (!ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1)) { atomicExch(&g_sm100_error, 21); break; }
         const uint32_t fb = ptx::smem_u32(&full_bar[s]);
         const uint32_t sA = smem_base + s * STAGE_BYTES;
         ptx::mbar_arrive_expect_tx(fb, STAGE_BYTES);
-        ptx::tma_load_2d(sA, &tmA, fb, kb * BK, m0);
-        ptx::tma_load_2d(sA + A_BYTES, &tmB, fb, kb * BK, n0);
+        ptx::tma_load_2d(sA, &tmA, fb, (kb0 + i) * BK, m0);
+        ptx::tma_load_2d(sA + A_BYTES, &tmB, fb, (kb0 + i) * BK, n0);
       }
     }
     __syncwarp();
   } else if (warp_idx == 1) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         if (!ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph)) { atomicExch(&g_sm100_error, 22); break; }
         ptx::tc_fence_after();
         const uint32_t sA = smem_base + s * STAGE_BYTES, sB = sA + A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)
           ptx::mma_bf16_ss(tmem, ptx::make_smem_desc_sw128(sA + k * 32, 16, 1024), ptx::make_smem_desc_sw128(sB + k * 32, 16, 1024), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+                           (i > 0 || k > 0) ? 1u : 0u);
         ptx::mma_commit(ptx::smem_u32(&empty_bar[s]));
       }
       ptx::mma_commit(ptx::smem_u32(&tmem_full_bar));
@@ -188,18 +195,58 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool ok = ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar), 0);
       if (!ok) atomicExch(&g_sm100_error, 24);
       ptx::tc_fence_after();
-      if (col_ok) {
-        uint32_t r[32];
-        if (p.num_kb > 0) {
-          ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32), r);
-          ptx::tc_wait_ld();
-        } else {
+      uint32_t r[32];
+      if (nkb > 0) {
+        ptx::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32), r);
+        ptx::tc_wait_ld();
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      bool mine = true;                                    // does this CTA run the epilogue?
+      if (gridDim.z > 1) {
+        // split-K: park the partial sums, count arrivals; only the tile's last CTA goes on (the others' sums are in L2 by then)
+        const long long slab = (long long)p.M * p.N;
+        if (row_ok && col_ok) {
+          float* dst = p.part + (long long)blockIdx.z * slab + (long long)m * p.N + n;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8)
+            if (n + 8 * g8 < H) {
+              reinterpret_cast<float4*>(dst + 8 * g8)[0] = make_float4(__uint_as_float(r[8 * g8]), __uint_as_float(r[8 * g8 + 1]), __uint_as_float(r[8 * g8 + 2]), __uint_as_float(r[8 * g8 + 3]));
+              reinterpret_cast<float4*>(dst + 8 * g8)[1] = make_float4(__uint_as_float(r[8 * g8 + 4]), __uint_as_float(r[8 * g8 + 5]), __uint_as_float(r[8 * g8 + 6]), __uint_as_float(r[8 * g8 + 7]));
+            }
         }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          unsigned int* cnt = p.tile_count + blockIdx.y * gridDim.x + blockIdx.x;
+          const unsigned int old = atomicAdd(cnt, 1u);
+          s_last = (old == gridDim.z - 1);
+          if (s_last) *cnt = 0u;                             // ready for the next step's launch
+        }
+        __syncthreads();
+        mine = s_last != 0;
+        if (mine && row_ok && col_ok) {
+          __threadfence();
+          for (int z = 0; z < (int)gridDim.z; ++z) {
+            if (z == (int)blockIdx.z) continue;
+            const float* src = p.part + (long long)z * slab + (long long)m * p.N + n;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8)
+              if (n + 8 * g8 < H) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(src + 8 * g8)), b = __ldcg(reinterpret_cast<const float4*>(src + 8 * g8) + 1);
+                r[8 * g8] = __float_as_uint(__uint_as_float(r[8 * g8]) + a.x); r[8 * g8 + 1] = __float_as_uint(__uint_as_float(r[8 * g8 + 1]) + a.y);
+                r[8 * g8 + 2] = __float_as_uint(__uint_as_float(r[8 * g8 + 2]) + a.z); r[8 * g8 + 3] = __float_as_uint(__uint_as_float(r[8 * g8 + 3]) + a.w);
+                r[8 * g8 + 4] = __float_as_uint(__uint_as_float(r[8 * g8 + 4]) + b.x); r[8 * g8 + 5] = __float_as_uint(__uint_as_float(r[8 * g8 + 5]) + b.y);
+                r[8 * g8 + 6] = __float_as_uint(__uint_as_float(r[8 * g8 + 6]) + b.z); r[8 * g8 + 7] = __float_as_uint(__uint_as_float(r[8 * g8 + 7]) + b.w);
+              }
+          }
+        }
+      }
+      if (col_ok && mine) {
         if (row_ok) {
-#pragma unroll 1
-          for (int g8 = 0; g8 < 4; ++g8) {                 // 8 units at a time
+#pragma unroll 4
+          for (int g8 = 0; g8 < 4; ++g8) {                 // 8 units at a time (unrolled: the four groups' loads go out together)
             const int u = n + 8 * g8;
             if (u >= H) break;
             const long long o = (long long)m * H + u;
@@ -266,7 +313,8 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int EPI>
-static int launch_step(cudaStream_t stream, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb, StepParams p) {
+static int launch_step(cudaStream_t stream, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb, StepParams p,
+                       int splits = 1) {
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmB, 0, sizeof(tmB));
@@ -278,13 +326,20 @@ static int launch_step(cudaStream_t stream, int M, int N, int K, const void* A, 
     if (rc) return rc;
   }
   p.M = M; p.N = N;
+  if (splits > 1 && p.num_kb >= 2) {
+    p.kb_per_split = (p.num_kb + splits - 1) / splits;
+    splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;      // no empty slice
+  } else {
+    splits = 1;
+    p.kb_per_split = p.num_kb;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     S2VT_CHECK_CUDA(cudaFuncSetAttribute(lstm_step_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ceil_div(N, BN), ceil_div(M, BM)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
+  cfg.gridDim = dim3(ceil_div(N, BN), ceil_div(M, BM), splits); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -337,14 +392,32 @@ extern "C" int s2vt_lstm_steps_fwd_bf16(void* stream, int T, int B, int H, int n
 //   gates, cells                  the forward stash
 //   w_hh_t  [H, 4H] bf16          W_hh^T (natural gate order along K)
 //   dgates  [T, B, 4H] bf16       out: pre-activation gradients, natural gate order (column g*H + u)
-//   dc_ws   [B, H] f32            scratch (running dL/dc)
+//   ws      >= s2vt_lstm_steps_bwd_ws_bytes(B, H): running dL/dc, split-K partial sums and tile counters
+// K = 4H runs over few output tiles (batch 256 x H 1000: 32), so the product is split over K until the step fills the machine.
+static int bwd_splits(int B, int H) {
+  const int tiles = ceil_div(H, BN) * ceil_div(B, BM);
+  int sp = 128 / (tiles > 0 ? tiles : 1);
+  const int num_kb = ceil_div(4 * H, BK);
+  if (sp > 8) sp = 8;
+  if (sp > num_kb / 2) sp = num_kb / 2;
+  return sp < 1 ? 1 : sp;
+}
+extern "C" int64_t s2vt_lstm_steps_bwd_ws_bytes(int B, int H) {
+  const int sp = bwd_splits(B, H);
+  return (int64_t)sizeof(float) * B * H * (1 + sp) + 4 * (int64_t)ceil_div(H, BN) * ceil_div(B, BM) + 512;
+}
 extern "C" int s2vt_lstm_steps_bwd_bf16(void* stream, int T, int B, int H, int dout_t0, const float* dout, const void* gates,
-                                        const float* cells, const void* w_hh_t, void* dgates, float* dc_ws) {
+                                        const float* cells, const void* w_hh_t, void* dgates, void* ws) {
   cudaStream_t s = (cudaStream_t)stream;
   S2VT_REQUIRE(T >= 0 && B > 0 && H > 0 && H % 8 == 0, "s2vt_lstm_steps_bwd_bf16: needs H %% 8 == 0 (H=%d)", H);
-  S2VT_REQUIRE(gates && cells && w_hh_t && dgates && dc_ws, "s2vt_lstm_steps_bwd_bf16: null pointer");
+  S2VT_REQUIRE(gates && cells && w_hh_t && dgates && ws, "s2vt_lstm_steps_bwd_bf16: null pointer");
   const long long BH = (long long)B * H;
+  const int sp = bwd_splits(B, H);
+  float* dc_ws = (float*)ws;
+  float* part = dc_ws + BH;
+  unsigned int* tile_count = (unsigned int*)(((uintptr_t)(part + (long long)sp * BH) + 255) & ~(uintptr_t)255);
   S2VT_CHECK_CUDA(cudaMemsetAsync(dc_ws, 0, sizeof(float) * BH, s));
+  S2VT_CHECK_CUDA(cudaMemsetAsync(tile_count, 0, 4 * (size_t)ceil_div(H, BN) * ceil_div(B, BM), s));
   for (int t = T - 1; t >= 0; --t) {
     StepParams p{};
     p.H = H;
@@ -354,8 +427,9 @@ extern "C" int s2vt_lstm_steps_bwd_bf16(void* stream, int T, int B, int H, int d
     p.c_prev = t > 0 ? cells + (long long)(t - 1) * BH : nullptr;
     p.dc = dc_ws;
     p.dgates = (__nv_bfloat16*)dgates + (long long)t * 4 * BH;
+    p.part = part; p.tile_count = tile_count;
     const void* A = t < T - 1 ? (const void*)((const __nv_bfloat16*)dgates + (long long)(t + 1) * 4 * BH) : nullptr;
-    int rc = launch_step<EPI_BWD>(s, B, H, 4 * H, A, 4 * H, w_hh_t, 4 * H, p);
+    int rc = launch_step<EPI_BWD>(s, B, H, 4 * H, A, 4 * H, w_hh_t, 4 * H, p, sp);
     if (rc) return rc;
   }
   return 0;

@@ -84,10 +84,11 @@ def lstm_steps_fwd(T, B, H, n_pre, pre, bias_il, w_hh_il, out, gates, cells):
 
 
 def lstm_steps_bwd(T, B, H, dout_t0, dout, gates, cells, w_hh_t, dgates):
-    dc = torch.empty(B, H, device=dgates.device)
+    lib = L.load()
+    ws = torch.empty(int(lib.s2vt_lstm_steps_bwd_ws_bytes(B, H)), dtype=torch.uint8, device=dgates.device)
     with ops._timed("lstm_steps_bwd_bf16", 2.0 * T * B * H * 4 * H, 4.0 * T * B * 5 * H + 2.0 * T * (B * 12 * H + 4 * H * H)):
-        rc = L.load().s2vt_lstm_steps_bwd_bf16(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
-                                               L.ptr(w_hh_t), L.ptr(dgates), L.ptr(dc))
+        rc = lib.s2vt_lstm_steps_bwd_bf16(L.stream_ptr(dgates.device), T, B, H, dout_t0, L.ptr(dout), L.ptr(gates), L.ptr(cells),
+                                               L.ptr(w_hh_t), L.ptr(dgates), L.ptr(ws))
     L.check(rc, "s2vt_lstm_steps_bwd_bf16")
 
 

@@ -91,6 +91,7 @@ SIGNATURES = {
     "s2vt_beam_search_f32": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp]),
     "s2vt_lstm_steps_fwd_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s2vt_lstm_steps_bwd_ws_bytes": (_i64, [_i, _i]),
     "s2vt_lstm_steps_bwd_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2vt_xgemm_ws_bytes": (_i64, [_i, _i, _i]),
     "s2vt_xgemm_f32": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, RowMap, _vp, _i, _vp]),
