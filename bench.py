@@ -405,9 +405,25 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_MIN_CTAS", "16")          # the 20-27 MB gradient buckets are bandwidth-bound: measured +4% at 8 GPUs
+        # NCCL logs to stdout by default and rank 0's stdout must carry ONE JSON line: send its log to stderr.  At level VERSION NCCL
+        # ignores NCCL_DEBUG_FILE (the banner "NCCL version ..." goes to stdout regardless), so that level is raised to WARN; on top of
+        # that, stdout is pointed at stderr while the communicator comes up.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"     # NCCL logs to stdout by default; rank 0's stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     numa_node = None
     if world > 1 and os.environ.get("S2VT_NUMA_BIND", "1") != "0":
         from s2vt_b200.dp import bind_to_local_numa

@@ -37,7 +37,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                  # (at VERSION the banner ignores NCCL_DEBUG_FILE and lands on stdout)
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     model = s2vt_b200.S2VT(CFG["V"], CFG["F"], CFG["L"], dim_hid=CFG["H"], dim_embed=CFG["E"], decode_precision=args.decode).to(dev).eval()
