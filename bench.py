@@ -353,6 +353,10 @@ def decode_run(s2vt_b200, dev, rank, world, sync_all, peaks):
         ms_ge, _ = timed(greedy_all, host, True)
         ms_be, _ = timed(beam_all, host, True)
     L_ = CFG["L"]
+    try:
+        dtraffic = json.load(open(os.path.join(ROOT, "profiles", "r02g_decode_dram_traffic.json")))
+    except Exception:
+        dtraffic = None
     gcap = world * NG / (ms_g / 1e3)
     # algorithmic work: SURVEY 8(d), 2.721 GFLOP per greedy caption; every fp32-grade product is three fp16 tensor-core passes
     tf = gcap / world * FLOP_PER_VIDEO_FWD / 1e12
@@ -368,7 +372,9 @@ def decode_run(s2vt_b200, dev, rank, world, sync_all, peaks):
                      "bit-identical to the reference on every golden (tests/test_gpu_model_parity.py)",
         "roofline": {"bound": "tensor", "kernel": "xgemm_kernel (all epilogues; whole greedy call)", "achieved": round(tf, 1),
                      "achieved_mma": round(3 * tf, 1), "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_sust"], 4),
-                     "frac_mma": round(3 * tf / peaks["tf_sust"], 4), "traffic": None,
+                     "frac_mma": round(3 * tf / peaks["tf_sust"], 4),
+                     "traffic": None if dtraffic is None else {k: v.get("dram_bytes_per_launch") for k, v in dtraffic.items() if isinstance(v, dict)},
+                     "traffic_source": None if dtraffic is None else "profiles/r02g_decode_dram_traffic.json (ncu --set full, per launch)",
                      "note": "achieved = 2.721 GFLOP per caption (SURVEY 8d) / time; achieved_mma counts the three fp16 passes per product. "
                              "A chain of 238 dependent step kernels + 79 vocab products per batch: in-kernel phase times in profiles/r02_trace_*.txt"},
     }
