@@ -12,9 +12,10 @@ from .data import DeviceFeatureStore, ids_to_sentence, predictions_to_dict
 from .lib import LIB_PATH, S2VTLibraryError, launch_count, load
 from .model import PARAM_ORDER, S2VT, S2VTModel
 from .optim import FusedAdam
+from .dp import DataParallelTrainer, GraphedLoopBody
 from .training import EarlyStopping, fit, validate
 
 BF16_TRAIN_READY = True     # bench.py: the tensor-core training path is the default for supported shapes
 
 __all__ = ["BF16_TRAIN_READY", "S2VT", "S2VTModel", "Att_Baseline", "ATT_PARAM_ORDER", "MaskCriterion", "FusedAdam", "DeviceFeatureStore", "ids_to_sentence", "predictions_to_dict", "EarlyStopping", "fit", "validate", "PARAM_ORDER", "load", "launch_count", "LIB_PATH",
-           "S2VTLibraryError"]
+           "S2VTLibraryError", "DataParallelTrainer", "GraphedLoopBody"]

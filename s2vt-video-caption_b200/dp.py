@@ -346,3 +346,56 @@ class DataParallelTrainer:
         ent = (graph, loss, n_launch, (feats, targets), exec_)
         self._graphs[key] = ent
         return ent
+
+
+class GraphedLoopBody:
+    """The reference's UNCHANGED train-loop body (train.py:116-127) captured once into a CUDA graph and replayed:
+
+        def body(feats, targets, masks):
+            optimizer.zero_grad()
+            loss = criterion(model(feats, targets[:, :-1], mode='train'), targets, masks)
+            loss.backward()
+            optimizer.step()
+            return loss
+        step = GraphedLoopBody(body, (feats, targets, masks), optimizer=optimizer)
+        loss = step(feats, targets, masks)          # copies the batch into the captured buffers, replays
+
+    What an eager step loses on this path is not host time but launch order and gaps on the device (1.73 ms against 1.34 ms for the
+    same kernels); a replayed graph gets them back without touching the body.  Requirements: fixed input shapes,
+    a FusedAdam optimizer (its step() keeps the step count / lr on the device while capturing) and no host reads (.item()) inside the
+    body.  The returned loss is the captured output tensor (overwritten by the next call)."""
+
+    def __init__(self, body, example_inputs, optimizer=None, warmup: int = 3):
+        self.body, self.opt = body, optimizer
+        self.static = [x.clone() if torch.is_tensor(x) else x for x in example_inputs]
+        dev = next(x.device for x in self.static if torch.is_tensor(x))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                        # (warm-up off the capture stream, as torch's CUDA-graph notes ask)
+            for _ in range(max(2, warmup)):
+                out = body(*self.static)
+                del out                                      # no autograd graph of a warm-up step may outlive it (AccumulateGrad streams)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        host_step = optimizer._flat["step"] if optimizer is not None and getattr(optimizer, "_flat", None) else None
+        if optimizer is not None and hasattr(optimizer, "sync_lr"):
+            optimizer.sync_lr()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = body(*self.static)
+        if host_step is not None:
+            optimizer._flat["step"] = host_step              # capturing enqueued nothing: the step happens at replay
+        self.out = self.out.detach() if torch.is_tensor(self.out) else self.out
+        self.replays = 0
+
+    def __call__(self, *inputs):
+        for s_, x in zip(self.static, inputs):
+            if torch.is_tensor(s_) and x.data_ptr() != s_.data_ptr():
+                s_.copy_(x, non_blocking=True)
+        if self.opt is not None and hasattr(self.opt, "sync_lr"):
+            self.opt.sync_lr()
+        self.graph.replay()
+        if self.opt is not None and hasattr(self.opt, "note_replayed_step"):
+            self.opt.note_replayed_step()
+        self.replays += 1
+        return self.out

@@ -214,6 +214,16 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         f = self._ensure_flat()
+        if f["g"].is_cuda and torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture (dp.GraphedLoopBody, or a user's own torch.cuda.graph around the loop body): nothing that
+            # changes from step to step may be a kernel argument, so take the route whose step count / lr / bias corrections live on
+            # the device (the one DataParallelTrainer uses)
+            self.gather_grads()
+            self.begin_step()
+            self.step_range(0, f["n"], grad_scale)
+            self.finish_step(grad_scale)
+            f["derived_ok"] = False
+            return loss
         for p, o in zip(f["params"], f["offsets"]):
             gv = f["g"][o:o + p.numel()].view(p.shape)
             if p.grad is None:

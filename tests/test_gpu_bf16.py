@@ -727,3 +727,47 @@ def test_step_engine_paper_sizing_vs_reference_golden(dev):
         rel = np.linalg.norm(gs.astype(np.float64) - rs) / max(1e-30, np.linalg.norm(rs.astype(np.float64)))
         print("grad %-24s rel-L2 err (sampled) %.3e" % (k, rel))
         assert rel <= 2e-2, k
+
+
+def test_graphed_loop_body_matches_eager_loop_body(dev):
+    """The reference's unchanged loop body (zero_grad, module forward, MaskCriterion, backward, optimizer.step) captured with
+    GraphedLoopBody: same losses and weights as running the body eagerly, lr changes between replays take effect."""
+    V, F, H, E, Lq, B = 203, 64, 128, 64, 8, 6
+    g = torch.Generator().manual_seed(31)
+    data = [(torch.randn(B, Lq, F, generator=g).to(dev), torch.randint(0, V, (B, Lq), generator=g).to(dev), torch.ones(B, Lq, device=dev))
+            for _ in range(3)]
+    out = {}
+    for graphed in (False, True):
+        torch.manual_seed(32)
+        model = s2vt_b200.S2VT(V, F, Lq, dim_hid=H, dim_embed=E, train_precision="bf16").to(dev)
+        opt = s2vt_b200.FusedAdam(model.parameters(), lr=1e-3)
+        opt.attach(model)
+        crit = s2vt_b200.MaskCriterion()
+
+        def body(f, t, m):
+            opt.zero_grad()
+            loss = crit(model(f, targets=t[:, :-1], mode="train"), t, m)
+            loss.backward()
+            opt.step()
+            return loss
+        losses = []
+        if graphed:
+            step = s2vt_b200.GraphedLoopBody(body, data[0], optimizer=opt, warmup=2)
+            n_warm = 2
+        else:
+            step, n_warm = body, 0
+            for _ in range(2):                       # the warm-up steps GraphedLoopBody runs on its example batch
+                float(body(*data[0]).item())
+        for i in range(6):
+            if i == 3:
+                opt.param_groups[0]["lr"] = 3e-4
+            losses.append(float(step(*data[i % 3]).item()))
+        torch.cuda.synchronize()
+        assert L.load().s2vt_device_error_flag(L.stream_ptr(dev)) == 0
+        out[graphed] = (losses, {k: p.detach().clone() for k, p in model.named_parameters()}, opt._flat["step"])
+    assert out[True][2] == out[False][2] == 8
+    for a, b in zip(out[True][0], out[False][0]):
+        assert abs(a - b) <= 2e-3 * abs(b), (out[True][0], out[False][0])
+    for k in out[True][1]:
+        a, b = out[True][1][k].double(), out[False][1][k].double()
+        assert (a - b).norm().item() <= 2e-3 * max(1e-30, b.norm().item()), k
