@@ -150,3 +150,29 @@ def test_profiler_detection_and_numa_binding_degrade_gracefully(monkeypatch):
     assert dp.bind_to_local_numa(0) is None or isinstance(dp.bind_to_local_numa(0), int)  # no GPU / no topology: None, never raises
     assert os.sched_getaffinity(0) <= before
     os.sched_setaffinity(0, before)
+
+
+def test_rank_sharded_batches_partition_the_epoch(tiny_dataset):
+    """fit() under torch.distributed: every rank draws the same permutation and takes every world-th batch of the first `usable`
+    ones -- the ranks' batches are disjoint, together they are the first `usable` batches, and every rank gets the same count."""
+    cf, fd, data = tiny_dataset
+    st = s2vt_b200.DeviceFeatureStore(cf, fd, max_len=6, mode="train", device="cpu")
+    bs, world = 1, 3
+    n_batches = (len(st) + bs - 1) // bs
+    usable = n_batches - n_batches % world
+    full = [b for _, _, b, _ in st.batches(bs, shuffle=True, generator=torch.Generator().manual_seed(7))]
+    per_rank = []
+    for r in range(world):
+        per_rank.append([b for _, _, b, _ in st.batches(bs, shuffle=True, generator=torch.Generator().manual_seed(7), only=(r, world, usable))])
+    assert len({len(x) for x in per_rank}) == 1 and len(per_rank[0]) == usable // world
+    merged = [per_rank[i % world][i // world] for i in range(usable)]
+    assert merged == full[:usable]
+
+
+def test_fused_adam_rejects_param_groups_and_keeps_flat_state_keys():
+    a, b = torch.nn.Parameter(torch.zeros(8)), torch.nn.Parameter(torch.zeros(8))
+    with pytest.raises(ValueError):
+        s2vt_b200.FusedAdam([{"params": [a]}, {"params": [b], "lr": 1e-2}])
+    opt = s2vt_b200.FusedAdam([a, b], lr=1e-3)
+    sd = opt.state_dict()                                 # before the first step there is no flat state yet: plain torch layout
+    assert "fused" not in sd and "param_groups" in sd
