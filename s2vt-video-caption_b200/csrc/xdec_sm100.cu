@@ -52,6 +52,7 @@ struct XParams {
   int M, N, K, num_kb;
   const float* a_inv;        // device scalars: 1/scale of each operand (powers of two)
   const float* b_inv;
+  const float* a_inv_row;    // optional [M]: one scale per row of A instead (the feature matrix: scaled and split in ONE pass)
   const float* bias;         // [N] (LSTM: used when pre == nullptr)
   // STORE
   float* C; RowMap cm; int accumulate; int c_vec;
@@ -238,7 +239,7 @@ xgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int q = warp_idx & 3, half = warp_idx >> 2;
     const int m = m0 + q * 32 + lane;
     const bool row_ok = m < p.M;
-    const float sc = (p.a_inv ? __ldg(p.a_inv) : 1.f) * (p.b_inv ? __ldg(p.b_inv) : 1.f);
+    const float sc = (p.a_inv_row ? (row_ok ? __ldg(p.a_inv_row + m) : 1.f) : (p.a_inv ? __ldg(p.a_inv) : 1.f)) * (p.b_inv ? __ldg(p.b_inv) : 1.f);
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const int nmain = p.num_kb < 3 ? p.num_kb : 3;
     pdl_wait();
@@ -485,6 +486,32 @@ __global__ void split_kernel(const float* __restrict__ x, long long rows, int co
     const __half lo = __float2half_rn(xs - __half2float(hi));
     planes[ro * out_ld + cc] = hi;
     planes[plane_stride + ro * out_ld + cc] = lo;
+  }
+}
+
+// One block per row: the row's own power-of-two scale (max |x| into [2^14, 2^15)), both planes and 1/scale -- a single pass over
+// the matrix (the per-tensor form needs the maximum first: two passes over 670 MB of features per 512 videos).
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int cols, long long ld, __half* __restrict__ planes,
+                                                         long long out_ld, long long plane_stride, float* __restrict__ inv_row) {
+  __shared__ float sh[8];
+  const long long r = blockIdx.x;
+  const float* src = x + r * ld;
+  float mx = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, fabsf(src[c]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = sh[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
+  const float s = scale_from_bits(__float_as_uint(mx));
+  if (threadIdx.x == 0) inv_row[r] = 1.f / s;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {          // (second read of the row: L1 / L2 hit)
+    const float xs = src[c] * s;
+    const __half hi = __float2half_rn(xs);
+    planes[r * out_ld + c] = hi;
+    planes[plane_stride + r * out_ld + c] = __float2half_rn(xs - __half2float(hi));
   }
 }
 
@@ -917,6 +944,7 @@ static inline long long rup(long long x, long long a) { return (x + a - 1) / a *
 
 struct Planes {            // an fp16 (hi, lo) operand: rows x k, leading dimension ld, planes `plane` elements apart
   const __half* p; long long ld; long long plane; const float* inv;
+  const float* inv_row = nullptr;     // per-row 1/scale instead of `inv` (A operands only)
 };
 
 static unsigned long long* g_trace_buf = nullptr;     // s2vt_xdec_set_trace: [max][8] stamps, one record per xgemm launch
@@ -932,7 +960,7 @@ static int launch_x(cudaStream_t st, int M, int N, int K, const Planes& A, const
   rc = make_tmap_planes(&tmB, B.p, (uint64_t)K, (uint64_t)N, (uint64_t)B.ld, (uint64_t)B.plane, BN);
   if (rc) return rc;
   p.M = M; p.N = N; p.K = K; p.num_kb = (K + BK - 1) / BK;
-  p.a_inv = A.inv; p.b_inv = B.inv;
+  p.a_inv = A.inv; p.b_inv = B.inv; p.a_inv_row = A.inv_row;
   if (g_trace_buf && g_trace_n < g_trace_max) {
     p.trace = g_trace_buf + 8 * (size_t)g_trace_n++;
     static int tbx = -1, tby = 0;
@@ -1206,6 +1234,7 @@ extern "C" int s2vt_xdec_prepare(void* stream, s2vt_xdec_cfg cfg, const float* c
 namespace {
 struct GreedyWs {
   float* inv; unsigned int* bits;
+  float* finv;                   // [L*B] per-row 1/scale of the feature planes
   __half *fa, *xp, *o1p, *h2p;
   float *xproj, *pre1, *pre2, *c1, *c2;
   int* sos;
@@ -1219,6 +1248,7 @@ GreedyWs carve_greedy(char* base, const Cfg& g, int B, int T1 /* vid_rnn steps *
   const size_t G = 4 * (size_t)g.HP, LB = (size_t)g.L * B;
   const int n_part = ceil_div(g.V, 128);
   w.inv = (float*)take(64); w.bits = (unsigned int*)take(64);
+  w.finv = (float*)take(4 * LB);
   w.fa = (__half*)take(2 * 2 * LB * g.FP);
   w.xproj = (float*)take(4 * LB * g.HP);
   w.xp = (__half*)take(2 * 2 * LB * g.HP);
@@ -1243,8 +1273,9 @@ int encode(cudaStream_t st, cudaStream_t sd, const Cfg& g, const Weights& W, con
   int rc;
   // features -> fp16 planes; xproj = feat_linear(feats), rows re-ordered batch-major -> time-major
   if (g.FP != g.F) S2VT_CHECK_CUDA(cudaMemsetAsync(w.fa, 0, 2 * 2 * (size_t)L * B * g.FP, st));
-  X_TRY(x_split(st, feats, (long long)B * L, g.F, g.F, 0, w.bits, 1.f, w.fa, g.FP, (long long)B * L * g.FP, w.inv));
-  Planes PF{w.fa, g.FP, (long long)B * L * g.FP, w.inv}, WF{W.feat, g.FP, (long long)HP * g.FP, W.inv + INV_FEAT};
+  split_rows_kernel<<<(unsigned)(B * L), 256, 0, st>>>(feats, g.F, g.F, w.fa, g.FP, (long long)B * L * g.FP, w.finv);
+  S2VT_CHECK_LAUNCH();
+  Planes PF{w.fa, g.FP, (long long)B * L * g.FP, nullptr, w.finv}, WF{W.feat, g.FP, (long long)HP * g.FP, W.inv + INV_FEAT};
   X_TRY(x_store(st, B * L, HP, g.FP, PF, WF, w.xproj, RowMap{L, (long long)HP, BH}, W.bf, 0));
   X_TRY(x_split(st, w.xproj, (long long)L * B, HP, HP, 0, w.bits + 1, 1.f, w.xp, HP, (long long)L * B * HP, w.inv + 1));
   Planes PX{w.xp, HP, (long long)L * B * HP, w.inv + 1}, WI1{W.ih1, HP, (long long)G * HP, W.inv + INV_IH1};
