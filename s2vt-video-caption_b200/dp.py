@@ -83,12 +83,28 @@ class GradAllReducer:
     """Averages a flat gradient buffer across ranks, one bucket at a time.  Device-agnostic (gloo on CPU in tests,
     NCCL on the GPUs): `ready(bucket)` may be called as backward progresses; `finish()` joins everything."""
 
-    def __init__(self, flat_grad: torch.Tensor, ranges: Dict[str, Tuple[int, int]], group=None, overlap: bool = True):
+    def __init__(self, flat_grad: torch.Tensor, ranges: Dict[str, Tuple[int, int]], group=None, overlap: bool = True,
+                 transport_dtype: Optional[torch.dtype] = None):
+        """transport_dtype=torch.bfloat16: a bucket crosses NVLink as bf16 (cast, all-reduce, cast back: half the bytes on the wire for
+        two extra passes over the bucket in HBM); the ranks still end with bit-identical gradients.  Default: fp32 as stored."""
         self.flat, self.ranges, self.group = flat_grad, ranges, group
+        self.transport_dtype = transport_dtype if flat_grad.is_cuda else None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat_grad.is_cuda
         self.overlap = overlap and self.cuda and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=flat_grad.device) if self.overlap else None
+        # Communication lanes: each lane = its own NCCL communicator + stream, and the buckets alternate between the lanes in the
+        # order backward releases them.  On one communicator the five all-reduces form a serial chain of latency-bound collectives
+        # (8-27 MB each at 150-210 GB/s, far below NVLink 5) that ends 0.2 ms after the step would; two lanes overlap neighbouring
+        # all-reduces (measured at 2 GPUs: 1.555 -> 1.498 ms per step; bf16 transport, by contrast, made it slower: 1.587).
+        # S2VT_COMM_GROUPS sets the number of lanes (default 2; 1 = the single chain).
+        self.lanes = [(self.comm_stream, group)]
+        n_lanes = max(1, int(os.environ.get("S2VT_COMM_GROUPS", "2")))
+        if self.overlap and group is None:
+            for _ in range(n_lanes - 1):
+                self.lanes.append((torch.cuda.Stream(device=flat_grad.device), dist.new_group(backend="nccl")))
+        self.n_released = 0                      # buckets alternate between the lanes in the order backward releases them
+        self.last_stream = self.comm_stream
         self.pending: List = []
         self.done: set = set()
         self.bytes_reduced = 0
@@ -104,12 +120,20 @@ class GradAllReducer:
         if self.overlap:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.flat.device))
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
+            cstream, cgroup = self.lanes[self.n_released % len(self.lanes)]
+            self.n_released += 1
+            self.last_stream = cstream
+            with torch.cuda.stream(cstream):
+                cstream.wait_event(ev)
                 from . import ops
                 if ops.MARKS is not None:                                          # tools/timeline_step.py
                     ops._mark("B all_reduce[%s %.1f MB]" % (bucket, view.numel() * 4 / 1e6))
-                dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group)      # NCCL averages in the collective
+                if self.transport_dtype is not None:
+                    wire = view.to(self.transport_dtype)
+                    dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=cgroup)
+                    view.copy_(wire)
+                else:
+                    dist.all_reduce(view, op=dist.ReduceOp.AVG, group=cgroup)      # NCCL averages in the collective
                 if ops.MARKS is not None:
                     ops._mark("E all_reduce[%s %.1f MB]" % (bucket, view.numel() * 4 / 1e6))
         else:
@@ -124,25 +148,30 @@ class GradAllReducer:
             if bname not in self.done:
                 self.ready(bname)
         if self.overlap:
-            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+            for cstream, _ in self.lanes:
+                torch.cuda.current_stream(self.flat.device).wait_stream(cstream)
         for work, view in self.pending:
             work.wait()
             view.mul_(1.0 / self.world)
         self.pending.clear()
         self.done.clear()
+        self.n_released = 0
 
 
 class DataParallelTrainer:
     """model + FusedAdam + gradient all-reduce: `step(feats, targets)` is the reference's train-loop body
     (train.py:116-127) on this rank's shard."""
 
-    def __init__(self, model, optimizer, group=None, overlap: bool = True, cuda_graph: Optional[bool] = None):
+    def __init__(self, model, optimizer, group=None, overlap: bool = True, cuda_graph: Optional[bool] = None,
+                 grad_transport_dtype: Optional[torch.dtype] = None):
         self.model, self.opt = model, optimizer
+        if grad_transport_dtype is None and os.environ.get("S2VT_GRAD_BF16") == "1":
+            grad_transport_dtype = torch.bfloat16
         f = optimizer._ensure_flat()
         names = [n for n, _ in model.named_parameters()]
         sizes = [p.numel() for p in f["params"]]
         self.ranges = bucket_ranges(names, f["offsets"], sizes, getattr(model, "DP_BUCKETS", None))
-        self.reducer = GradAllReducer(f["g"], self.ranges, group=group, overlap=overlap)
+        self.reducer = GradAllReducer(f["g"], self.ranges, group=group, overlap=overlap, transport_dtype=grad_transport_dtype)
         # S2VT_EARLY_OUT_WGRAD=1: backward produces out_linear's weight gradient (the first, biggest bucket) ahead of the serial chain so
         # that its all-reduce starts ~0.3 ms earlier.  Measured at 2 GPUs: 1.602 ms per step against 1.561 without -- the product costs
         # the chain more than the earlier all-reduce saves, and its NCCL CTAs then compete with the sweeps' clusters -- so it is off.
@@ -196,7 +225,7 @@ class DataParallelTrainer:
         if self.reducer.overlap:
             # behind this bucket's all-reduce, but on a stream of its own: the next bucket's all-reduce does not wait for this update
             ev = torch.cuda.Event()
-            ev.record(self.reducer.comm_stream)
+            ev.record(self.reducer.last_stream)          # the stream this bucket's all-reduce went to
             ev_here = torch.cuda.Event()                 # (the all-reduce may have been started earlier than this call: ':reduce')
             ev_here.record(torch.cuda.current_stream(self.reducer.flat.device))
             if self._adam_stream is None:
