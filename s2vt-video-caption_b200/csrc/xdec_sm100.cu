@@ -754,6 +754,8 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
   const int base = v * bw, s = base + w;
   const int n = n_part * KC;
   const bool was_done = done[v] != 0;              // (read by every thread before thread 0 may set it below: barrier in between)
+  const bool stamp = (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0);        // debug: phase times of one CTA (S2VT_XDEC_EVENTS=1)
+  if (stamp) n_done[2] = (int)(ptx::globaltimer_ns() & 0x7fffffff);
   __shared__ float m_key[KC], m_pen[KC];
   __shared__ int m_tok[KC], m_len[KC], m_fin[KC], m_nb;
   if (threadIdx.x < bw) {                          // the video's queue state, fetched in parallel for the serial step below
@@ -836,6 +838,7 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
     }
   }
   __syncthreads();
+  if (stamp) n_done[3] = (int)(ptx::globaltimer_ns() & 0x7fffffff);
   // ---- 2. the PriorityQueue step of S2VTModel.py:186-238 (see beam_select_kernel)
   if (threadIdx.x == 0) {
     s_was_done = was_done ? 1 : 0;
@@ -891,6 +894,7 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
     __threadfence_block();
   }
   __syncthreads();
+  if (stamp) n_done[4] = (int)(ptx::globaltimer_ns() & 0x7fffffff);
   // ---- 3. the new slot d = base + w: history, answer so far, state from its parent
   const int d = s;
   if (lane < KC) row_thr[(long long)d * KC + lane] = 0u;            // next depth's candidate bounds start from "none"
@@ -907,17 +911,32 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
       if (w == 0) out_tokens[(long long)v * D1 + q] = (q < Ln) ? t : -1;
     }
   }
-  for (int u = lane; u < HP; u += 32) {
-    a1[(long long)d * HP + u] = x[(long long)ps * 2 * HP + u];
-    a1[a1_plane + (long long)d * HP + u] = x[x_plane + (long long)ps * 2 * HP + u];
-    c1[(long long)d * HP + u] = c1n[(long long)ps * HP + u];
-    c2[(long long)d * HP + u] = c2n[(long long)ps * HP + u];
+  // 16-byte copies (HP is a multiple of 8: rows of fp16 planes and fp32 cells are 16-byte aligned); all loads of a row first
+  {
+    const int nh = HP / 8, nf = HP / 4;                     // uint4 per plane row / per cell row
+    const uint4* xs0 = reinterpret_cast<const uint4*>(x + (long long)ps * 2 * HP);
+    const uint4* xs1 = reinterpret_cast<const uint4*>(x + x_plane + (long long)ps * 2 * HP);
+    const uint4* hs0 = reinterpret_cast<const uint4*>(h2n + (long long)ps * HP);
+    const uint4* hs1 = reinterpret_cast<const uint4*>(h2n + h2n_plane + (long long)ps * HP);
+    uint4* ad0 = reinterpret_cast<uint4*>(a1 + (long long)d * HP);
+    uint4* ad1 = reinterpret_cast<uint4*>(a1 + a1_plane + (long long)d * HP);
+    // (x[:, HP:] is written for slot d while another warp may still read x[:, :HP] of slot d as ITS parent: different columns)
+    uint4* xd0 = reinterpret_cast<uint4*>(x + (long long)d * 2 * HP + HP);
+    uint4* xd1 = reinterpret_cast<uint4*>(x + x_plane + (long long)d * 2 * HP + HP);
+    for (int u = lane; u < nh; u += 32) {
+      const uint4 v0 = xs0[u], v1 = xs1[u], v2 = hs0[u], v3 = hs1[u];
+      ad0[u] = v0; ad1[u] = v1; xd0[u] = v2; xd1[u] = v3;
+    }
+    const uint4* cs1 = reinterpret_cast<const uint4*>(c1n + (long long)ps * HP);
+    const uint4* cs2 = reinterpret_cast<const uint4*>(c2n + (long long)ps * HP);
+    uint4* cd1 = reinterpret_cast<uint4*>(c1 + (long long)d * HP);
+    uint4* cd2 = reinterpret_cast<uint4*>(c2 + (long long)d * HP);
+    for (int u = lane; u < nf; u += 32) {
+      const uint4 v0 = cs1[u], v1 = cs2[u];
+      cd1[u] = v0; cd2[u] = v1;
+    }
   }
-  // (x[:, HP:] is written for slot d while another warp may still read x[:, :HP] of slot d as ITS parent: different columns)
-  for (int u = lane; u < HP; u += 32) {
-    x[(long long)d * 2 * HP + HP + u] = h2n[(long long)ps * HP + u];
-    x[x_plane + (long long)d * 2 * HP + HP + u] = h2n[h2n_plane + (long long)ps * HP + u];
-  }
+  if (stamp) n_done[5] = (int)(ptx::globaltimer_ns() & 0x7fffffff);
 }
 
 // slot 0 of each video <- the video's encode state; the other slots start from zero
@@ -1515,6 +1534,10 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
     fprintf(stderr, "[xdec beam depth 10] vid_rnn step %.1f us, word_rnn step %.1f us, vocab + top-k %.1f us, queue/merge/re-order %.1f us\n",
             1e3f * ms[0], 1e3f * ms[1], 1e3f * ms[2], 1e3f * ms[3]);
+    int st4[8];
+    if (cudaMemcpy(st4, w.n_done, sizeof(st4), cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "[xdec beam, last depth, one CTA of the bookkeeping kernel] merge %.2f us, queue step %.2f us, histories + state copies %.2f us\n",
+              1e-3f * (st4[3] - st4[2]), 1e-3f * (st4[4] - st4[3]), 1e-3f * (st4[5] - st4[4]));
     for (int i = 0; i < 5; ++i) cudaEventDestroy(tev[i]);
   }
 #undef X_STAMP
