@@ -632,7 +632,8 @@ def main():
         api_graphed = {"value": round(world * B / (tg_.item() / n_api / 1e3), 2), "unit": "videos/s", "ms_per_step": round(tg_.item() / n_api, 4),
                        "ratio_to_value": round(world * B / (tg_.item() / n_api / 1e3) / value, 4), "loss": float(lg_.item()),
                        "what": "the same body (zero_grad, module forward, MaskCriterion, backward, FusedAdam.step) captured once with "
-                               "s2vt_b200.GraphedLoopBody and replayed; every step copies its batch (84 MB) into the captured buffers"}
+                               "s2vt_b200.GraphedLoopBody and replayed; every step copies its batch (84 MB) into the captured buffers" +
+                               ("; no gradient all-reduce on this path (single-process loop body)" if world > 1 else "")}
         del gstep
 
     # ---- decode: greedy / beam captions per second on this rank's videos
