@@ -536,74 +536,6 @@ __global__ void keys_to_tokens_kernel(int M, const unsigned long long* __restric
 }
 
 // ------------------------------------------------------------------ beam bookkeeping
-// One warp per slot: merge the per-tile (max, sum exp, top-KC) partials into log_softmax values of the row's best kc tokens.
-// Each lane keeps the best KC of its share of the candidates (most lists are empty: the epilogue filters against the row's running
-// bound), then kc rounds pick the best lane head (highest value, lowest index on ties) and pop it.
-__global__ void beam_combine_kernel(int S, int n_part, int kc, const float* __restrict__ ms, const float* __restrict__ tv,
-                                    const int* __restrict__ ti, float* __restrict__ cand_lp, int* __restrict__ cand_tok) {
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (s >= S) return;
-  const int n = n_part * KC;
-  float mx = -INFINITY;
-  for (int j = lane; j < n_part; j += 32) mx = fmaxf(mx, ms[2 * ((long long)s * n_part + j)]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-  for (int j = lane; j < n_part; j += 32) {
-    const long long o = 2 * ((long long)s * n_part + j);
-    sum += ms[o + 1] * expf(ms[o] - mx);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float logsum = logf(sum);
-  // stage the row's candidates in shared memory (independent, coalesced loads), then select from there
-  extern __shared__ float sh_all[];
-  float* shv = sh_all + (size_t)(threadIdx.x >> 5) * 2 * n;
-  int* shi = reinterpret_cast<int*>(shv + n);
-  for (int j = lane; j < n; j += 32) { shi[j] = ti[(long long)s * n + j]; shv[j] = tv[(long long)s * n + j]; }
-  __syncwarp();
-  float lv[KC];
-  int li[KC];
-#pragma unroll
-  for (int q = 0; q < KC; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
-  for (int j = lane; j < n; j += 32) {
-    const int id = shi[j];
-    if (id == 0x7fffffff) continue;
-    const float v = shv[j];
-    if (v > lv[KC - 1] || (v == lv[KC - 1] && id < li[KC - 1])) {
-      lv[KC - 1] = v; li[KC - 1] = id;
-#pragma unroll
-      for (int q = KC - 1; q > 0; --q) {
-        if (lv[q] > lv[q - 1] || (lv[q] == lv[q - 1] && li[q] < li[q - 1])) {
-          const float fv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = fv;
-          const int iv = li[q]; li[q] = li[q - 1]; li[q - 1] = iv;
-        }
-      }
-    }
-  }
-  for (int r = 0; r < kc; ++r) {
-    float bv = lv[0];
-    int bi = li[0], bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; bl = ol; }
-    }
-    if (lane == 0) {
-      cand_lp[(long long)s * kc + r] = (bv - mx) - logsum;        // log_softmax as torch computes it: (z - max) - log(sum exp)
-      cand_tok[(long long)s * kc + r] = bi != 0x7fffffff ? bi : 0;
-    }
-    if (lane == bl && bi != 0x7fffffff) {                         // pop the winner's head
-#pragma unroll
-      for (int q = 0; q < KC - 1; ++q) { lv[q] = lv[q + 1]; li[q] = li[q + 1]; }
-      lv[KC - 1] = -INFINITY; li[KC - 1] = 0x7fffffff;
-    }
-  }
-}
-
 struct BeamMeta { float* key; int* tok; int* len; int* fin; int* hist; };
 
 __global__ void beam_init_kernel(int B, int bw, int D1, int sos, BeamMeta m, int* nbeam, int* done, int64_t* out_tokens, int* out_len) {
@@ -622,122 +554,16 @@ __global__ void beam_init_kernel(int B, int bw, int D1, int sos, BeamMeta m, int
   out_len[v] = 1;
 }
 
-// The PriorityQueue step of S2VTModel.py:186-238, one thread per video.  `topk` is the reference's expansion width (only
-// used to count queue entries for the stop rule); `kc` <= topk candidates per slot are available, which is enough because
-// at most beam_width entries leave the queue per depth.
-__global__ void beam_select_kernel(int B, int bw, int topk, int kc, int D1, int eos, const float* __restrict__ len_pen,
-                                   BeamMeta old_, BeamMeta new_, const float* __restrict__ cand_lp, const int* __restrict__ cand_tok,
-                                   int* __restrict__ nbeam, int* __restrict__ done, int* __restrict__ was_done, int* __restrict__ parent,
-                                   int* __restrict__ out_len, int* __restrict__ n_done) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= B) return;
-  const int base = v * bw;
-  was_done[v] = done[v];
-  if (done[v]) {
-    for (int j = 0; j < bw; ++j) {
-      const int s = base + j;
-      new_.key[s] = old_.key[s]; new_.tok[s] = old_.tok[s]; new_.len[s] = old_.len[s]; new_.fin[s] = old_.fin[s];
-      parent[s] = s;
-    }
-    return;
-  }
-  const int nb = nbeam[v];
-  int ptr[32];
-  long long count = 0;
-  for (int j = 0; j < nb; ++j) { ptr[j] = 0; count += old_.fin[base + j] ? 1 : topk; }
-  const bool last = (count <= bw);
-  const int take = count < bw ? (int)count : bw;
-  for (int r = 0; r < take; ++r) {
-    float bestk = INFINITY; int bj = -1;
-    for (int j = 0; j < nb; ++j) {
-      const int s = base + j;
-      float k;
-      if (old_.fin[s]) { if (ptr[j] > 0) continue; k = old_.key[s]; }
-      else {
-        if (ptr[j] >= kc) continue;
-        k = -(cand_lp[(long long)s * kc + ptr[j]] / len_pen[old_.len[s] + 1]);
-      }
-      if (bj < 0 || k < bestk) { bestk = k; bj = j; }
-    }
-    const int d = base + r;
-    if (bj < 0) {                    // cannot happen while kc >= min(topk, bw); keep the slot inert
-      new_.key[d] = INFINITY; new_.tok[d] = 0; new_.len[d] = 1; new_.fin[d] = 0; parent[d] = d;
-      continue;
-    }
-    const int s = base + bj;
-    const int ln = old_.len[s];
-    // token histories are not copied here: slot d inherits its parent's row in beam_hist_kernel (one warp per slot)
-    if (old_.fin[s]) {
-      new_.key[d] = old_.key[s]; new_.tok[d] = old_.tok[s]; new_.len[d] = ln; new_.fin[d] = 1;
-    } else {
-      const int tk = cand_tok[(long long)s * kc + ptr[bj]];
-      new_.key[d] = bestk; new_.tok[d] = tk; new_.len[d] = ln + 1; new_.fin[d] = (tk == eos) ? 1 : 0;
-    }
-    ptr[bj] += 1;
-    parent[d] = s;
-    if (r == 0) out_len[v] = new_.len[d];
-  }
-  for (int r = take; r < bw; ++r) {
-    const int d = base + r;
-    new_.key[d] = INFINITY; new_.tok[d] = 0; new_.len[d] = 1; new_.fin[d] = 0;
-    parent[d] = d;
-  }
-  nbeam[v] = take;
-  if (last) { done[v] = 1; atomicAdd(n_done, 1); }
-}
-
-// Token histories after a selection: slot d's row = its parent's row (+ the token just appended); slot 0 of a video (the head
-// of its queue) is also the video's answer so far.  grid = S slots, one warp each.  `was_done` = done[] before this selection.
-__global__ void beam_hist_kernel(int bw, int D1, BeamMeta old_, BeamMeta new_, const int* __restrict__ parent, const int* __restrict__ was_done,
-                                 int64_t* __restrict__ out_tokens) {
-  const int d = blockIdx.x, v = d / bw;
-  if (was_done[v]) return;                                    // frozen video: its answer is final, its rows are never read again
-  const bool unused = (new_.key[d] == INFINITY);
-  const int s = parent[d];
-  const bool fresh = !unused && !old_.fin[s];                 // a live hypothesis extended by new_.tok[d]
-  const int Ln = new_.len[d];
-  for (int q = threadIdx.x; q < D1; q += 32) {
-    int t = unused ? -1 : old_.hist[(long long)s * D1 + q];
-    if (fresh && q == Ln - 1) t = new_.tok[d];
-    new_.hist[(long long)d * D1 + q] = t;
-    if (d == v * bw) out_tokens[(long long)v * D1 + q] = (q < Ln) ? t : -1;
-  }
-}
-
-// Per-slot state after a depth, re-ordered by parent.  Plane buffers hold fp16 (hi, lo) rows of HP elements.
-//   p=0: a1[s]      <- x[parent][0:HP]      (h1', both planes)       p=1: c1[s] <- c1n[parent]
-//   p=2: x[s][HP:]  <- h2n[parent]          (both planes)            p=3: c2[s] <- c2n[parent]
-__global__ void beam_gather_kernel(int S, int HP, const int* __restrict__ parent,
-                                   __half* __restrict__ a1, long long a1_plane, __half* __restrict__ x, long long x_plane,
-                                   const __half* __restrict__ h2n, long long h2n_plane,
-                                   float* __restrict__ c1, const float* __restrict__ c1n, float* __restrict__ c2, const float* __restrict__ c2n,
-                                   unsigned int* __restrict__ row_thr) {
-  const int s = blockIdx.x, pl = blockIdx.y;
-  const long long ps = parent[s];
-  if (pl == 0) {
-    if (threadIdx.x < KC) row_thr[(long long)s * KC + threadIdx.x] = 0u;      // the next depth's candidate bounds start from "none"
-    for (int u = threadIdx.x; u < HP; u += blockDim.x) {
-      a1[(long long)s * HP + u] = x[ps * 2 * HP + u];
-      a1[a1_plane + (long long)s * HP + u] = x[x_plane + ps * 2 * HP + u];
-    }
-  } else if (pl == 1) {
-    for (int u = threadIdx.x; u < HP; u += blockDim.x) c1[(long long)s * HP + u] = c1n[ps * HP + u];
-  } else if (pl == 2) {
-    for (int u = threadIdx.x; u < HP; u += blockDim.x) {
-      x[(long long)s * 2 * HP + HP + u] = h2n[ps * HP + u];
-      x[x_plane + (long long)s * 2 * HP + HP + u] = h2n[h2n_plane + ps * HP + u];
-    }
-  } else {
-    for (int u = threadIdx.x; u < HP; u += blockDim.x) c2[(long long)s * HP + u] = c2n[ps * HP + u];
-  }
-}
-
 // ---- one depth's bookkeeping in ONE kernel: a CTA per video, a warp per beam slot.
-//   1. every warp merges its slot's per-tile partials into the slot's best kc (log-prob, token) pairs (beam_combine_kernel's code)
-//   2. thread 0 runs the PriorityQueue step for the video (beam_select_kernel's code) on the candidates in shared memory
-//   3. every warp builds its NEW slot: token history, answer so far, and the LSTM state copied from the parent slot (the code of
-//      beam_hist_kernel and beam_gather_kernel); the candidate bounds of the next depth are reset
-// Replaces four launches per depth (merge 28 us, queue 12 us, histories 5 us, re-order 9 us when run one after the other).
+//   1. every warp merges its slot's per-tile (max, sum exp, top-KC) partials into the slot's best kc (log-prob, token) pairs: each
+//      lane keeps the best KC of its share of the candidates (most lists are empty: the epilogue filters against the row's running
+//      bound), then kc rounds pick the best lane head (highest value, lowest index on ties) and pop it
+//   2. thread 0 runs the PriorityQueue step of S2VTModel.py:186-238 for the video on the candidates in shared memory.  `topk` is
+//      the reference's expansion width (only used to count queue entries for the stop rule); kc <= topk candidates per slot are
+//      enough because at most beam_width entries leave the queue per depth
+//   3. every warp builds its NEW slot: token history (its parent's row + the token just appended; slot 0 is also the video's answer
+//      so far) and the LSTM state copied from the parent slot; the candidate bounds of the next depth are reset
+// (Four separate launches in the first version: merge 28 us, queue 12 us, histories 5 us, re-order 9 us one after the other.)
 __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int eos, int HP, int n_part, const float* __restrict__ len_pen,
                                    BeamMeta old_, BeamMeta new_, const float* __restrict__ ms, const float* __restrict__ tv,
                                    const int* __restrict__ ti, int* __restrict__ nbeam, int* __restrict__ done, int* __restrict__ n_done,
@@ -839,7 +665,7 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
   }
   __syncthreads();
   if (stamp) n_done[3] = (int)(ptx::globaltimer_ns() & 0x7fffffff);
-  // ---- 2. the PriorityQueue step of S2VTModel.py:186-238 (see beam_select_kernel)
+  // ---- 2. the PriorityQueue step of S2VTModel.py:186-238
   if (threadIdx.x == 0) {
     s_was_done = was_done ? 1 : 0;
     if (was_done) {
@@ -1388,8 +1214,8 @@ extern "C" int s2vt_xdec_greedy(void* stream, s2vt_xdec_cfg cfg, const void* wbu
 namespace {
 struct BeamWs {
   __half *a1, *x, *h2n;
-  float *c1, *c1n, *c2, *c2n, *ms, *tv, *cand_lp;
-  int *ti, *cand_tok, *nbeam, *done, *was_done, *parent, *n_done;
+  float *c1, *c1n, *c2, *c2n, *ms, *tv;
+  int *ti, *nbeam, *done, *n_done;
   unsigned int* row_thr;
   xd::BeamMeta meta[2];
   size_t bytes;
@@ -1409,9 +1235,7 @@ BeamWs carve_beam(char* base, const Cfg& g, int B, int bw, int D1) {
   w.ms = (float*)take(4 * 2 * S * n_part2);
   w.tv = (float*)take(4 * S * n_part2 * KC);
   w.ti = (int*)take(4 * S * n_part2 * KC);
-  w.cand_lp = (float*)take(4 * S * KC);
-  w.cand_tok = (int*)take(4 * S * KC);
-  w.nbeam = (int*)take(4 * (size_t)B); w.done = (int*)take(4 * (size_t)B); w.was_done = (int*)take(4 * (size_t)B); w.parent = (int*)take(4 * S);
+  w.nbeam = (int*)take(4 * (size_t)B); w.done = (int*)take(4 * (size_t)B);
   w.n_done = (int*)take(64);
   w.row_thr = (unsigned int*)take(4 * S * KC);
   for (int i = 0; i < 2; ++i) {
