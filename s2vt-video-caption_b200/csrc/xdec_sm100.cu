@@ -572,13 +572,11 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
                                    const __half* __restrict__ h2n, long long h2n_plane,
                                    float* __restrict__ c1, const float* __restrict__ c1n, float* __restrict__ c2, const float* __restrict__ c2n,
                                    unsigned int* __restrict__ row_thr) {
-  extern __shared__ float sh_all[];
   __shared__ float s_lp[KC * KC];
   __shared__ int s_tok[KC * KC];
   __shared__ int s_parent[KC], s_was_done;
   const int v = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int base = v * bw, s = base + w;
-  const int n = n_part * KC;
   const bool was_done = done[v] != 0;              // (read by every thread before thread 0 may set it below: barrier in between)
   const bool stamp = (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0);        // debug: phase times of one CTA (S2VT_XDEC_EVENTS=1)
   if (stamp) n_done[2] = (int)(ptx::globaltimer_ns() & 0x7fffffff);
@@ -604,40 +602,41 @@ __global__ void beam_finish_kernel(int B, int bw, int topk, int kc, int D1, int 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float logsum = logf(sum);
-    float* shv = sh_all + (size_t)w * 2 * n;
-    int* shi = reinterpret_cast<int*>(shv + n);
-    // (eight independent loads in flight per lane and array: the loop is otherwise one L2 round trip per iteration)
-    for (int j0 = lane; j0 < n; j0 += 32 * 8) {
-      int ids[8];
-      float vs[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int jj = j0 + 32 * u;
-        ids[u] = jj < n ? __ldcg(ti + (long long)s * n + jj) : 0x7fffffff;
-        vs[u] = jj < n ? __ldcg(tv + (long long)s * n + jj) : -INFINITY;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int jj = j0 + 32 * u;
-        if (jj < n) { shi[jj] = ids[u]; shv[jj] = vs[u]; }
-      }
-    }
-    __syncwarp();
+    // Candidate lists are sorted and mostly EMPTY (the vocab epilogue filters against the row's running bound): a lane first looks at
+    // the head of each of its lists (one round trip for all of them), then reads only the non-empty ones.
     float lv[KC];
     int li[KC];
 #pragma unroll
     for (int q = 0; q < KC; ++q) { lv[q] = -INFINITY; li[q] = 0x7fffffff; }
-    for (int j = lane; j < n; j += 32) {
-      const int id = shi[j];
-      if (id == 0x7fffffff) continue;
-      const float val = shv[j];
-      if (val > lv[KC - 1] || (val == lv[KC - 1] && id < li[KC - 1])) {
-        lv[KC - 1] = val; li[KC - 1] = id;
+    constexpr int MAXL = 16;                                 // lists per lane handled per pass (n_part <= 512 in one pass)
+    for (int l0 = lane; l0 < n_part; l0 += 32 * MAXL) {
+      int head[MAXL];
 #pragma unroll
-        for (int q = KC - 1; q > 0; --q) {
-          if (lv[q] > lv[q - 1] || (lv[q] == lv[q - 1] && li[q] < li[q - 1])) {
-            const float fv = lv[q]; lv[q] = lv[q - 1]; lv[q - 1] = fv;
-            const int iv = li[q]; li[q] = li[q - 1]; li[q - 1] = iv;
+      for (int u = 0; u < MAXL; ++u) {
+        const int l = l0 + 32 * u;
+        head[u] = l < n_part ? __ldcg(ti + ((long long)s * n_part + l) * KC) : 0x7fffffff;
+      }
+#pragma unroll
+      for (int u = 0; u < MAXL; ++u) {
+        if (head[u] == 0x7fffffff) continue;
+        const long long o = ((long long)s * n_part + (l0 + 32 * u)) * KC;
+        int ids[KC];
+        float vs[KC];
+#pragma unroll
+        for (int q = 0; q < KC; ++q) { ids[q] = __ldcg(ti + o + q); vs[q] = __ldcg(tv + o + q); }
+#pragma unroll
+        for (int q = 0; q < KC; ++q) {
+          const int id = ids[q];
+          const float val = vs[q];
+          if (id != 0x7fffffff && (val > lv[KC - 1] || (val == lv[KC - 1] && id < li[KC - 1]))) {
+            lv[KC - 1] = val; li[KC - 1] = id;
+#pragma unroll
+            for (int qq = KC - 1; qq > 0; --qq) {
+              if (lv[qq] > lv[qq - 1] || (lv[qq] == lv[qq - 1] && li[qq] < li[qq - 1])) {
+                const float fv = lv[qq]; lv[qq] = lv[qq - 1]; lv[qq - 1] = fv;
+                const int iv = li[qq]; li[qq] = li[qq - 1]; li[qq - 1] = iv;
+              }
+            }
           }
         }
       }
@@ -1292,12 +1291,6 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
   const Planes WH1{W.hh1, HP, (long long)G * HP, W.inv + INV_HH1}, WC2{W.cat2, 2 * HP, (long long)G * 2 * HP, W.inv + INV_CAT2};
   const Planes WO{W.out, HP, (long long)g.V * HP, W.inv + INV_OUT};
   const int n_part2 = 2 * ceil_div(g.V, 128);                 // candidate lists per row: one per tile and epilogue warp group
-  const size_t finish_smem = (size_t)beam_width * n_part2 * KC * 8;      // per slot: the row's candidates (values + indices)
-  S2VT_REQUIRE(finish_smem <= 200 * 1024, "s2vt_xdec_beam: vocabulary x beam width too large for the candidate merge (%zu bytes of shared memory)", finish_smem);
-  if (finish_smem > 48 * 1024)
-    S2VT_CHECK_CUDA(cudaFuncSetAttribute(beam_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  // keep the SMs' shared-memory carve-out where the GEMM kernels around it need it (a different carve-out drains the SM first)
-  S2VT_CHECK_CUDA(cudaFuncSetAttribute(beam_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int chunk = 0;
   // S2VT_XDEC_EVENTS=1 (debug): CUDA events around the four kernels of depth 10, printed after the call
   static int want_events = -1;
@@ -1332,7 +1325,7 @@ extern "C" int s2vt_xdec_beam(void* stream, s2vt_xdec_cfg cfg, const void* wbuf,
       X_TRY((launch_x<128, EPI_BEAM>(st, S, g.V, HP, A, WO, p)));
     }
     X_STAMP(3);
-    beam_finish_kernel<<<B, 32 * beam_width, finish_smem, st>>>(B, beam_width, topk, kc, D1, g.eos, HP, n_part2, len_pen, mo, mn, w.ms, w.tv, w.ti,
+    beam_finish_kernel<<<B, 32 * beam_width, 0, st>>>(B, beam_width, topk, kc, D1, g.eos, HP, n_part2, len_pen, mo, mn, w.ms, w.tv, w.ti,
                                                                   w.nbeam, w.done, w.n_done, out_tokens, out_len, w.a1, SH, w.x, 2 * SH, w.h2n, SH,
                                                                   w.c1, w.c1n, w.c2, w.c2n, w.row_thr);
     S2VT_CHECK_LAUNCH();
