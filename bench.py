@@ -391,7 +391,13 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["B"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-resident timed loop and the end-to-end loop")
+    ap.add_argument("--model", default="s2vt", choices=["s2vt", "att"],
+                    help="att: BASELINE configs[4], the attention_baseline.py encoder-decoder (tools/bench_att.py; train videos/s only)")
     args = ap.parse_args()
+    if args.model == "att" and args.impl == "ours":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_att
+        return bench_att.main(["--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--precision", args.precision] if args.precision in ("bf16", "fp32") else []))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

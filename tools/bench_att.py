@@ -23,7 +23,7 @@ import s2vt_b200
 from bench import CFG, synth_batch
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--api", action="store_true")
@@ -82,8 +82,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item() / args.steps
     if rank == 0:
-        print(json.dumps({"metric": "Att_Baseline train videos/sec", "value": round(world * CFG["B"] / (ms / 1e3), 1), "ms_per_step": round(ms, 3),
-                          "n_gpus": world, "precision": args.precision, "batch_per_gpu": CFG["B"], "loss": float(loss.item()),
+        print(json.dumps({"metric": "Att_Baseline train videos/sec", "value": round(world * CFG["B"] / (ms / 1e3), 1), "unit": "videos/s",
+                          "ms_per_step": round(ms, 3), "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 6), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[4]: attention_baseline.py encoder-decoder, batch %d/GPU, MSVD shape 80x4096, "
+                                                 "V=13000, H=E=512, random init" % CFG["B"], "global_batch": world * CFG["B"], "parallelism": "dp%d" % world},
+                          "precision": args.precision, "batch_per_gpu": CFG["B"], "loss": float(loss.item()),
                           "path": "DataParallelTrainer (forward_loss, graph replays %d)" % trainer.replays if trainer is not None else "module + MaskCriterion + FusedAdam.step, eager",
                           "launches_total": int(s2vt_b200.launch_count())}))
     if world > 1:
