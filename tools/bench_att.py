@@ -29,7 +29,8 @@ def main(argv=None):
     ap.add_argument("--api", action="store_true")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
-    args = ap.parse_args()
+    ap.add_argument("--gpus", type=int, default=None, help="(informational: the launcher decides the world size)")
+    args = ap.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
